@@ -1,0 +1,754 @@
+// Fused inverse-warp + SSIM/L1 photometric loss, forward and backward, plus the stand-alone
+// SSIM / photometric-loss kernels that share the same tile code (sm_100a).
+//
+// One CTA owns a TH x TW tile of target pixels.
+//   forward : phase 1 fills shared-memory planes x = syn*valid, y = tgt*valid for the tile plus a
+//             1-pixel halo (back-project -> project -> bilinear gather, all in registers), phase 2
+//             evaluates the 3x3 SSIM statistics from shared memory in vertical strips and writes the
+//             loss map / block partial sums.  No intermediate ever reaches HBM.
+//   backward: phase A refills x, y for a 2-pixel halo, phase B recomputes the SSIM statistics at every
+//             centre of the 1-pixel halo and stores three coefficient planes per channel, phase C
+//             gathers them (adjoint of reflect-pad + box filter), applies the sampler / projection
+//             chain rule and emits grad_depth (one owner thread per pixel, no atomics), grad_src
+//             (red.global.add) and per-CTA grad_P partials (deterministic second pass).
+//
+// Forward arithmetic follows oracle/warp_photo_oracle.c operation for operation, which reproduces the
+// reference (view_synthesis.py:34-78, F.grid_sample, losses.py:23-37, 111-115) bit for bit.
+#include "common.cuh"
+
+namespace e2e {
+
+#define C1F 1.0e-4f
+#define C2F 9.0e-4f
+
+enum { MODE_WARP = 0, MODE_DIRECT = 1 };
+
+struct WPParams {
+    // inputs
+    const float *depth, *inv_K, *K, *T;
+    ImgView src, tgt;          // WARP: source / target image.  DIRECT: x / y.
+    int B, C, H, W;            // C = channels of the tensors (DIRECT may be != 3; kernel planes = B*C/CK)
+    int border, use_mask;
+    float eps, wm1, hm1, half_w, half_h;
+    DivC dW, dH, d9, d3;
+    // forward outputs (nullable)
+    float *syn, *valid, *pix, *ssim, *loss_map, *partial;
+    // backward
+    const float *g_loss_map, *g_ssim, *g_scalar;
+    float g_scale;
+    float *g_depth;
+    ImgViewW g_src;
+    float *gP_partial;
+    float *g_x, *g_y;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Camera constants of one batch element, staged once per CTA: cam[0..8] = inv_K[:3,:3],
+// cam[9..20] = P = (K @ T)[:3, :] with the k-loop accumulated in order (unfused), like at::bmm's
+// small-matrix path (view_synthesis.py:57).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_camera(const WPParams &p, int b, float *cam)
+{
+    const int t = threadIdx.x;
+    if (t < 9) {
+        cam[t] = p.inv_K[b * 16 + (t / 3) * 4 + (t % 3)];
+    } else if (t < 21) {
+        const int e = t - 9, i = e >> 2, j = e & 3;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc = xadd(acc, xmul(p.K[b * 16 + i * 4 + k], p.T[b * 16 + k * 4 + j]));
+        cam[t] = acc;
+    }
+}
+
+struct Proj {
+    float r0, r1, r2;      // inv_K[:3,:3] @ [x, y, 1]
+    float X0, X1, X2;      // camera point
+    float c0, c1, c2, z;   // P @ [X;1], z = c2 + eps
+    float gx, gy, valid;   // normalised grid coordinate, validity
+};
+
+__device__ __forceinline__ void project_pixel(const float *cam, const WPParams &p, int x, int y, float d, Proj &o)
+{
+    const float fx = (float)x, fy = (float)y;
+    // sgemm k-loop (k = 0,1,2) then * depth               view_synthesis.py:36-38
+    o.r0 = xadd(xfma(cam[1], fy, xmul(cam[0], fx)), cam[2]);
+    o.r1 = xadd(xfma(cam[4], fy, xmul(cam[3], fx)), cam[5]);
+    o.r2 = xadd(xfma(cam[7], fy, xmul(cam[6], fx)), cam[8]);
+    o.X0 = xmul(d, o.r0);
+    o.X1 = xmul(d, o.r1);
+    o.X2 = xmul(d, o.r2);
+    const float *P = cam + 9;                              // view_synthesis.py:59
+    o.c0 = xadd(xfma(P[2], o.X2, xfma(P[1], o.X1, xmul(P[0], o.X0))), P[3]);
+    o.c1 = xadd(xfma(P[6], o.X2, xfma(P[5], o.X1, xmul(P[4], o.X0))), P[7]);
+    o.c2 = xadd(xfma(P[10], o.X2, xfma(P[9], o.X1, xmul(P[8], o.X0))), P[11]);
+    o.z = xadd(o.c2, p.eps);                               // :60
+    const float u = xdiv(o.c0, o.z), v = xdiv(o.c1, o.z);
+    o.gx = xmul(xsub(xdivc(u, p.dW), 0.5f), 2.0f);         // :66-68
+    o.gy = xmul(xsub(xdivc(v, p.dH), 0.5f), 2.0f);
+    o.valid = (fabsf(o.gx) <= 1.0f && fabsf(o.gy) <= 1.0f) ? 1.0f : 0.0f;   // :70-71 (NaN -> 0)
+}
+
+// Bilinear sampling set-up, align_corners=False (ATen GridSamplerKernel.cpp, vectorised CPU path).
+struct Samp {
+    float ix, iy;              // after padding handling
+    float nw, ne, sw, se;      // weights of taps (y0,x0) (y0,x1) (y1,x0) (y1,x1)
+    int x0, y0;
+    bool inx0, inx1, iny0, iny1;
+    float mx, my;              // d(clamped)/d(unclamped): 0 where the border clamp is active
+};
+
+__device__ __forceinline__ void sampler_setup(const WPParams &p, float gx, float gy, Samp &s)
+{
+    float ix = xfma(xadd(gx, 1.0f), p.half_w, -0.5f);
+    float iy = xfma(xadd(gy, 1.0f), p.half_h, -0.5f);
+    s.mx = 1.0f;
+    s.my = 1.0f;
+    if (p.border) {
+        s.mx = (ix > 0.0f && ix < p.wm1) ? 1.0f : 0.0f;    // clip_coordinates_set_grad
+        s.my = (iy > 0.0f && iy < p.hm1) ? 1.0f : 0.0f;
+        ix = fminf(p.wm1, fmaxf(0.0f, ix));                // NaN clamps to 0
+        iy = fminf(p.hm1, fmaxf(0.0f, iy));
+    }
+    const float xw = floorf(ix), yn = floorf(iy);
+    const float w = xsub(ix, xw), e = xsub(1.0f, w), n = xsub(iy, yn), so = xsub(1.0f, n);
+    s.nw = xmul(so, e);
+    s.ne = xmul(so, w);
+    s.sw = xmul(n, e);
+    s.se = xmul(n, w);
+    s.ix = ix;
+    s.iy = iy;
+    // float comparisons so that NaN / huge coordinates are simply out of bounds
+    s.inx0 = (xw >= 0.0f) && (xw <= p.wm1);
+    s.inx1 = (xw >= -1.0f) && (xw <= p.wm1 - 1.0f);
+    s.iny0 = (yn >= 0.0f) && (yn <= p.hm1);
+    s.iny1 = (yn >= -1.0f) && (yn <= p.hm1 - 1.0f);
+    s.x0 = (s.inx0 || s.inx1) ? (int)xw : 0;
+    s.y0 = (s.iny0 || s.iny1) ? (int)yn : 0;
+}
+
+__device__ __forceinline__ void gather_taps(const ImgView &im, int b, const Samp &s, int ch, float v[4])
+{
+    const long long base = (long long)b * im.sb + (long long)ch * im.sc;
+    const long long r0 = base + (long long)s.y0 * im.sh, r1 = r0 + im.sh;
+    const long long c0 = (long long)s.x0 * im.sw, c1 = c0 + im.sw;
+    v[0] = (s.inx0 && s.iny0) ? __ldg(im.p + r0 + c0) : 0.0f;
+    v[1] = (s.inx1 && s.iny0) ? __ldg(im.p + r0 + c1) : 0.0f;
+    v[2] = (s.inx0 && s.iny1) ? __ldg(im.p + r1 + c0) : 0.0f;
+    v[3] = (s.inx1 && s.iny1) ? __ldg(im.p + r1 + c1) : 0.0f;
+}
+
+__device__ __forceinline__ float interp(const float v[4], const Samp &s)
+{
+    return xfma(v[3], s.se, xfma(v[2], s.sw, xfma(v[1], s.ne, xmul(v[0], s.nw))));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory tile: NPL planes of RH x RP floats covering image rows [oy, oy+RH), cols [ox, ox+RP).
+// reflect_fixup() fills the one-pixel ring just outside the image (row -1 <- row 1, row H <- row H-2,
+// same for columns; corners via columns-then-rows), i.e. nn.ReflectionPad2d(1) (losses.py:18).
+// ------------------------------------------------------------------------------------------------
+template <int NPL, int RH, int RP>
+__device__ __forceinline__ void reflect_fixup(float *pl, int oy, int ox, int H, int W)
+{
+    const bool touches = (oy < 0) || (ox < 0) || (oy + RH > H) || (ox + RP > W);
+    if (!touches) return;   // uniform per CTA
+    __syncthreads();
+    // columns: image col -1 and col W, for in-image rows
+    for (int i = threadIdx.x; i < NPL * RH * 2; i += blockDim.x) {
+        const int side = i & 1, r = (i >> 1) % RH, k = (i >> 1) / RH;
+        const int y = oy + r;
+        if (y < 0 || y >= H) continue;
+        const int lc = side ? (W - ox) : (-1 - ox);
+        const int ls = side ? lc - 2 : lc + 2;
+        if (lc < 0 || lc >= RP || ls < 0 || ls >= RP) continue;
+        pl[(k * RH + r) * RP + lc] = pl[(k * RH + r) * RP + ls];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPL * RP * 2; i += blockDim.x) {
+        const int side = i & 1, c = (i >> 1) % RP, k = (i >> 1) / RP;
+        const int x = ox + c;
+        if (x < -1 || x > W) continue;
+        const int lr = side ? (H - oy) : (-1 - oy);
+        const int ls = side ? lr - 2 : lr + 2;
+        if (lr < 0 || lr >= RH || ls < 0 || ls >= RH) continue;
+        pl[(k * RH + lr) * RP + c] = pl[(k * RH + ls) * RP + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact-order 3x3 window sums for NP vertically adjacent centres (one channel).
+// `wx`, `wy` point at the top-left sample of the first centre's window; S[p] = {Sx, Sy, Sxx, Syy, Sxy}
+// accumulated in avg_pool2d's order (kh outer, kw inner, running fp32 sum).
+// ------------------------------------------------------------------------------------------------
+template <int NP, int RP>
+__device__ __forceinline__ void window_sums(const float *wx, const float *wy, float (&S)[NP][5])
+{
+#pragma unroll
+    for (int r = 0; r < NP + 2; r++) {
+        float a[3], b[3], aa[3], bb[3], ab[3];
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++) {
+            a[dx] = wx[r * RP + dx];
+            b[dx] = wy[r * RP + dx];
+            aa[dx] = xmul(a[dx], a[dx]);
+            bb[dx] = xmul(b[dx], b[dx]);
+            ab[dx] = xmul(a[dx], b[dx]);
+        }
+#pragma unroll
+        for (int pp = 0; pp < NP; pp++) {
+            const int k = r - pp;   // row of centre pp's window
+            if (k < 0 || k > 2) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+                if (k == 0 && dx == 0) {
+                    S[pp][0] = a[0]; S[pp][1] = b[0]; S[pp][2] = aa[0]; S[pp][3] = bb[0]; S[pp][4] = ab[0];
+                } else {
+                    S[pp][0] = xadd(S[pp][0], a[dx]);
+                    S[pp][1] = xadd(S[pp][1], b[dx]);
+                    S[pp][2] = xadd(S[pp][2], aa[dx]);
+                    S[pp][3] = xadd(S[pp][3], bb[dx]);
+                    S[pp][4] = xadd(S[pp][4], ab[dx]);
+                }
+            }
+        }
+    }
+}
+
+struct SsimVals {
+    float mux, muy, A1, A2, B1, B2, n, dn, Q, sraw, s;
+};
+
+__device__ __forceinline__ void ssim_finish(const float S[5], const DivC d9, SsimVals &o)
+{
+    const float mux = xdivc(S[0], d9), muy = xdivc(S[1], d9);                  // losses.py:27-28
+    const float mxx = xmul(mux, mux), myy = xmul(muy, muy), mxy = xmul(mux, muy);
+    const float vx = xsub(xdivc(S[2], d9), mxx);                                // :30-32
+    const float vy = xsub(xdivc(S[3], d9), myy);
+    const float vxy = xsub(xdivc(S[4], d9), mxy);
+    o.A1 = xadd(xmul(xmul(2.0f, mux), muy), C1F);                               // :34
+    o.A2 = xadd(xmul(2.0f, vxy), C2F);
+    o.B1 = xadd(xadd(mxx, myy), C1F);                                           // :35
+    o.B2 = xadd(xadd(vx, vy), C2F);
+    o.n = xmul(o.A1, o.A2);
+    o.dn = xmul(o.B1, o.B2);
+    o.Q = xdiv(o.n, o.dn);
+    o.sraw = xmul(xsub(1.0f, o.Q), 0.5f);                                       // :37  (/2 is exact)
+    o.s = o.sraw < 0.0f ? 0.0f : (o.sraw > 1.0f ? 1.0f : o.sraw);               // NaN propagates
+    o.mux = mux;
+    o.muy = muy;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase 1: fill x / y planes for the region.  WARP: x = syn (*valid), y = tgt (*valid).
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int CK, int RH, int RP, int HALO, int TH, int TW>
+__device__ __forceinline__ void fill_region(const WPParams &p, const float *cam, int b, int ch0, int ty0, int tx0,
+                                            float *sx, float *sy, bool write_outputs)
+{
+    const int oy = ty0 - HALO, ox = tx0 - HALO;
+    for (int i = threadIdx.x; i < RH * RP; i += blockDim.x) {
+        const int hy = i / RP, hx = i - hy * RP;
+        const int y = oy + hy, x = ox + hx;
+        if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
+        if (MODE == MODE_WARP) {
+            const float d = __ldg(p.depth + ((long long)b * p.H + y) * p.W + x);
+            Proj pr;
+            project_pixel(cam, p, x, y, d, pr);
+            Samp s;
+            sampler_setup(p, pr.gx, pr.gy, s);
+            const bool centre = write_outputs && hy >= HALO && hy < HALO + TH && hx >= HALO && hx < HALO + TW;
+            const long long pixi = ((long long)b * p.H + y) * p.W + x;
+            if (centre) {
+                if (p.valid) p.valid[pixi] = pr.valid;
+                if (p.pix) { p.pix[pixi * 2] = pr.gx; p.pix[pixi * 2 + 1] = pr.gy; }
+            }
+            const long long tbase = (long long)b * p.tgt.sb + (long long)y * p.tgt.sh + (long long)x * p.tgt.sw;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                float v[4];
+                gather_taps(p.src, b, s, ch, v);
+                const float o = interp(v, s);
+                const float t = __ldg(p.tgt.p + tbase + ch * p.tgt.sc);
+                sx[(ch * RH + hy) * RP + hx] = p.use_mask ? xmul(o, pr.valid) : o;    // train_depth.py:714-715
+                sy[(ch * RH + hy) * RP + hx] = p.use_mask ? xmul(t, pr.valid) : t;
+                if (centre && p.syn) p.syn[(((long long)b * 3 + ch) * p.H + y) * p.W + x] = o;
+            }
+        } else {
+            const long long xb = (long long)b * p.src.sb + (long long)y * p.src.sh + (long long)x * p.src.sw;
+            const long long yb = (long long)b * p.tgt.sb + (long long)y * p.tgt.sh + (long long)x * p.tgt.sw;
+#pragma unroll
+            for (int ch = 0; ch < CK; ch++) {
+                sx[(ch * RH + hy) * RP + hx] = __ldg(p.src.p + xb + (long long)(ch0 + ch) * p.src.sc);
+                sy[(ch * RH + hy) * RP + hx] = __ldg(p.tgt.p + yb + (long long)(ch0 + ch) * p.tgt.sc);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// Forward kernel
+// ================================================================================================
+template <int MODE, int CK, int TH, int TW, int NT>
+__global__ void __launch_bounds__(NT) warp_photo_fwd_kernel(const __grid_constant__ WPParams p)
+{
+    constexpr int RH = TH + 2, RP = TW + 2;
+    constexpr int NP = TH * TW / NT;               // centres per thread (vertical strip)
+    static_assert(TH * TW % NT == 0 && NT % TW == 0 && (NT / TW) * NP == TH, "tile / thread mapping");
+    __shared__ float sx[CK * RH * RP];
+    __shared__ float sy[CK * RH * RP];
+    __shared__ float cam[24];
+    __shared__ float red[NT / 32];
+
+    const int planes_per_b = (MODE == MODE_DIRECT) ? p.C / CK : 1;
+    const int b = blockIdx.z / planes_per_b, ch0 = (blockIdx.z % planes_per_b) * CK;
+    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+
+    if (MODE == MODE_WARP) {
+        stage_camera(p, b, cam);
+        __syncthreads();
+    }
+    fill_region<MODE, CK, RH, RP, 1, TH, TW>(p, cam, b, ch0, ty0, tx0, sx, sy, true);
+    reflect_fixup<CK, RH, RP>(sx, ty0 - 1, tx0 - 1, p.H, p.W);
+    reflect_fixup<CK, RH, RP>(sy, ty0 - 1, tx0 - 1, p.H, p.W);
+    __syncthreads();
+
+    const int col = threadIdx.x % TW, rg = threadIdx.x / TW;
+    const int x = tx0 + col;
+    float ssum[NP], lsum[NP];
+#pragma unroll
+    for (int ch = 0; ch < CK; ch++) {
+        float S[NP][5];
+        const float *wx = sx + (ch * RH + rg * NP) * RP + col;
+        const float *wy = sy + (ch * RH + rg * NP) * RP + col;
+        window_sums<NP, RP>(wx, wy, S);
+#pragma unroll
+        for (int pp = 0; pp < NP; pp++) {
+            SsimVals v;
+            ssim_finish(S[pp], p.d9, v);
+            const float cx = wx[(pp + 1) * RP + 1], cy = wy[(pp + 1) * RP + 1];
+            const float l1 = fabsf(xsub(cy, cx));                                // losses.py:112
+            const int y = ty0 + rg * NP + pp;
+            if (p.ssim && y < p.H && x < p.W)
+                p.ssim[(((long long)b * p.C + ch0 + ch) * p.H + y) * p.W + x] = v.s;
+            if (ch == 0) { ssum[pp] = v.s; lsum[pp] = l1; }
+            else { ssum[pp] = xadd(ssum[pp], v.s); lsum[pp] = xadd(lsum[pp], l1); }
+        }
+    }
+    if (CK == 3 && (p.loss_map || p.partial)) {
+        float acc = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NP; pp++) {
+            const int y = ty0 + rg * NP + pp;
+            if (y < p.H && x < p.W) {
+                const float sm = xdivc(ssum[pp], p.d3), lm = xdivc(lsum[pp], p.d3);   // .mean(1, True)
+                const float l = xadd(xmul(0.85f, sm), xmul(0.15f, lm));               // losses.py:115
+                if (p.loss_map) p.loss_map[((long long)b * p.H + y) * p.W + x] = l;
+                acc += l;
+            }
+        }
+        if (p.partial) {
+            const float tot = block_sum(acc, red);
+            if (threadIdx.x == 0) p.partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+        }
+    }
+}
+
+// Deterministic final reduction of per-CTA partial sums: out[0] = sum(partial[0..n)) * scale.
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float *partial, long long n, double scale, float *out)
+{
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i];
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = sh[threadIdx.x];
+        acc = warp_sum_d(acc);
+        if (threadIdx.x == 0) out[0] = (float)(acc * scale);
+    }
+}
+
+// grad_P[b][e] = sum over the CTAs of batch element b of partial[cta][e]  (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) reduce_gP_kernel(const float *partial, int ctas_per_b, float *gP)
+{
+    __shared__ double sh[8];
+    const int b = blockIdx.x / 12, e = blockIdx.x % 12;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < ctas_per_b; i += blockDim.x) acc += (double)partial[((long long)b * ctas_per_b + i) * 12 + e];
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += sh[i];
+        gP[b * 12 + e] = (float)t;
+    }
+}
+
+// ================================================================================================
+// Backward kernel
+// ================================================================================================
+__device__ __forceinline__ float upstream_loss_grad(const WPParams &p, int b, int y, int x)
+{
+    if (p.g_loss_map) return __ldg(p.g_loss_map + ((long long)b * p.H + y) * p.W + x);
+    if (p.g_ssim) return 0.0f;                       // stand-alone SSIM backward with only grad_ssim
+    return (p.g_scalar ? __ldg(p.g_scalar) : 1.0f) * p.g_scale;
+}
+
+template <int MODE, int CK, int TH, int TW, int NT, bool NEED_GY>
+__global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constant__ WPParams p)
+{
+    constexpr int RH2 = TH + 4, RP2 = TW + 4;      // x / y region (2-pixel halo)
+    constexpr int RH1 = TH + 2, RP1 = TW + 2;      // centre region (1-pixel halo)
+    constexpr int NG = NEED_GY ? 4 : 3;            // coefficient planes per channel
+    constexpr int NPB = RH1 / 3;                   // centres per strip in phase B
+    constexpr int NPC = TH * TW / NT;              // owners per thread in phase C
+    static_assert(RH1 % 3 == 0 && TH * TW % NT == 0 && NT % TW == 0 && (NT / TW) * NPC == TH, "tile / thread mapping");
+    extern __shared__ float smem[];
+    float *sx = smem;                              // [CK][RH2][RP2]
+    float *sy = sx + CK * RH2 * RP2;
+    float *G = sy + CK * RH2 * RP2;                // [CK][NG][RH1][RP1]
+    float *cam = G + CK * NG * RH1 * RP1;          // 24
+    float *red = cam + 24;                         // NT/32 * 12
+
+    const int planes_per_b = (MODE == MODE_DIRECT) ? p.C / CK : 1;
+    const int b = blockIdx.z / planes_per_b, ch0 = (blockIdx.z % planes_per_b) * CK;
+    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const float invC = 1.0f / (float)p.C;
+
+    if (MODE == MODE_WARP) {
+        stage_camera(p, b, cam);
+        __syncthreads();
+    }
+    // ---- phase A ---------------------------------------------------------------------------
+    fill_region<MODE, CK, RH2, RP2, 2, TH, TW>(p, cam, b, ch0, ty0, tx0, sx, sy, false);
+    reflect_fixup<CK, RH2, RP2>(sx, ty0 - 2, tx0 - 2, p.H, p.W);
+    reflect_fixup<CK, RH2, RP2>(sy, ty0 - 2, tx0 - 2, p.H, p.W);
+    __syncthreads();
+
+    // ---- phase B: coefficient planes at every centre of the 1-pixel halo ----------------------
+    for (int task = threadIdx.x; task < 3 * RP1; task += NT) {
+        const int cg = task / RP1, cc = task - cg * RP1;      // strip cg covers centre rows cg*NPB .. +NPB-1
+        const int cx = tx0 - 1 + cc;
+#pragma unroll
+        for (int ch = 0; ch < CK; ch++) {
+            float S[NPB][5];
+            const float *wx = sx + (ch * RH2 + cg * NPB) * RP2 + cc;
+            const float *wy = sy + (ch * RH2 + cg * NPB) * RP2 + cc;
+            window_sums<NPB, RP2>(wx, wy, S);
+#pragma unroll
+            for (int pp = 0; pp < NPB; pp++) {
+                const int cr = cg * NPB + pp, cy = ty0 - 1 + cr;
+                float ga = 0.f, gb = 0.f, gc = 0.f, gay = 0.f;
+                if (cy >= 0 && cy < p.H && cx >= 0 && cx < p.W) {
+                    SsimVals v;
+                    ssim_finish(S[pp], p.d9, v);
+                    float gs = 0.85f * invC * upstream_loss_grad(p, b, cy, cx);
+                    if (p.g_ssim) gs += __ldg(p.g_ssim + (((long long)b * p.C + ch0 + ch) * p.H + cy) * p.W + cx);
+                    if (!(v.sraw >= 0.0f && v.sraw <= 1.0f)) gs = 0.0f;       // clamp passes gradient on [0,1]
+                    const float rdn = 1.0f / v.dn;
+                    const float dA = v.A2 - v.A1, dB = v.B2 - v.B1;
+                    const float h = (-0.5f / 9.0f) * gs;                       // d ssim/dQ = -1/2, box filter 1/9
+                    ga = h * (2.0f * v.muy * dA - v.Q * 2.0f * v.mux * dB) * rdn;
+                    gb = h * (-v.Q * v.B1) * rdn;
+                    gc = h * (2.0f * v.A1) * rdn;
+                    if (NEED_GY) gay = h * (2.0f * v.mux * dA - v.Q * 2.0f * v.muy * dB) * rdn;
+                }
+                float *g = G + ((ch * NG) * RH1 + cr) * RP1 + cc;
+                g[0] = ga;
+                g[RH1 * RP1] = gb;
+                g[2 * RH1 * RP1] = gc;
+                if (NEED_GY) g[3 * RH1 * RP1] = gay;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: owners ---------------------------------------------------------------------
+    const int col = threadIdx.x % TW, rg = threadIdx.x / TW;
+    const int x = tx0 + col;
+    // column multiplicities of the folded reflect padding (centre col x+dx contributes wcol[dx+1] times)
+    float wcol[3];
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+        const int cx = x + dx;
+        float w = (cx >= 0 && cx < p.W) ? 1.0f : 0.0f;
+        if (dx != 0 && ((cx == 0 && x == 1) || (cx == p.W - 1 && x == p.W - 2))) w += 1.0f;
+        wcol[dx + 1] = w;
+    }
+    float gP[12];
+#pragma unroll
+    for (int e = 0; e < 12; e++) gP[e] = 0.f;
+
+#pragma unroll
+    for (int pp = 0; pp < NPC; pp++) {
+        const int row = rg * NPC + pp, y = ty0 + row;
+        const bool inside = (y < p.H && x < p.W);
+        float wrow[3];
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+            const int cy = y + dy;
+            float w = (cy >= 0 && cy < p.H) ? 1.0f : 0.0f;
+            if (dy != 0 && ((cy == 0 && y == 1) || (cy == p.H - 1 && y == p.H - 2))) w += 1.0f;
+            wrow[dy + 1] = w;
+        }
+        const float gl = inside ? upstream_loss_grad(p, b, y, x) : 0.0f;
+        const float gl1 = 0.15f * invC * gl;
+        float gsyn[CK];
+#pragma unroll
+        for (int ch = 0; ch < CK; ch++) {
+            float acc[NG];
+#pragma unroll
+            for (int k = 0; k < NG; k++) acc[k] = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++) {
+#pragma unroll
+                for (int k = 0; k < NG; k++) {
+                    const float *g = G + ((ch * NG + k) * RH1 + row + dy) * RP1 + col;
+                    const float rs = wcol[0] * g[0] + wcol[1] * g[1] + wcol[2] * g[2];
+                    acc[k] += wrow[dy] * rs;
+                }
+            }
+            const float xj = sx[(ch * RH2 + row + 2) * RP2 + col + 2], yj = sy[(ch * RH2 + row + 2) * RP2 + col + 2];
+            const float df = xj - yj;
+            const float sg = (df > 0.f) ? 1.f : ((df < 0.f) ? -1.f : 0.f);
+            const float gxj = acc[0] + 2.0f * xj * acc[1] + yj * acc[2] + gl1 * sg;
+            gsyn[ch] = gxj;
+            if (MODE == MODE_DIRECT && inside) {
+                const long long o = (((long long)b * p.C + ch0 + ch) * p.H + y) * p.W + x;
+                if (p.g_x) p.g_x[o] = gxj;
+                if (NEED_GY && p.g_y) p.g_y[o] = acc[NG - 1] + 2.0f * yj * acc[1] + xj * acc[2] - gl1 * sg;
+            }
+        }
+        if (MODE == MODE_WARP && inside) {
+            const long long pixi = ((long long)b * p.H + y) * p.W + x;
+            const float d = __ldg(p.depth + pixi);
+            Proj pr;
+            project_pixel(cam, p, x, y, d, pr);
+            Samp s;
+            sampler_setup(p, pr.gx, pr.gy, s);
+            float gix = 0.f, giy = 0.f;
+            const float ex = 1.0f - (s.ix - floorf(s.ix)), wxx = s.ix - floorf(s.ix);
+            const float ey = 1.0f - (s.iy - floorf(s.iy)), wyy = s.iy - floorf(s.iy);
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const float gsy = p.use_mask ? gsyn[ch] * pr.valid : gsyn[ch];
+                float v[4];
+                gather_taps(p.src, b, s, ch, v);
+                gix += gsy * ((v[1] - v[0]) * ey + (v[3] - v[2]) * wyy);
+                giy += gsy * ((v[2] - v[0]) * ex + (v[3] - v[1]) * wxx);
+                if (p.g_src.p) {
+                    const long long base = (long long)b * p.g_src.sb + (long long)ch * p.g_src.sc;
+                    const long long r0 = base + (long long)s.y0 * p.g_src.sh, r1 = r0 + p.g_src.sh;
+                    const long long c0 = (long long)s.x0 * p.g_src.sw, c1 = c0 + p.g_src.sw;
+                    if (s.inx0 && s.iny0) atomicAdd(p.g_src.p + r0 + c0, gsy * s.nw);
+                    if (s.inx1 && s.iny0) atomicAdd(p.g_src.p + r0 + c1, gsy * s.ne);
+                    if (s.inx0 && s.iny1) atomicAdd(p.g_src.p + r1 + c0, gsy * s.sw);
+                    if (s.inx1 && s.iny1) atomicAdd(p.g_src.p + r1 + c1, gsy * s.se);
+                }
+            }
+            // sample position -> pixel coordinate -> camera point        
+            const float gu = gix * s.mx * (p.half_w * 2.0f / p.wm1);
+            const float gv = giy * s.my * (p.half_h * 2.0f / p.hm1);
+            const float rz = 1.0f / pr.z;
+            const float gc0 = gu * rz, gc1 = gv * rz;
+            const float gc2 = -(gu * pr.c0 + gv * pr.c1) * rz * rz;
+            const float *P = cam + 9;
+            const float q0 = P[0] * pr.r0 + P[1] * pr.r1 + P[2] * pr.r2;
+            const float q1 = P[4] * pr.r0 + P[5] * pr.r1 + P[6] * pr.r2;
+            const float q2 = P[8] * pr.r0 + P[9] * pr.r1 + P[10] * pr.r2;
+            p.g_depth[pixi] = gc0 * q0 + gc1 * q1 + gc2 * q2;
+            gP[0] += gc0 * pr.X0; gP[1] += gc0 * pr.X1; gP[2] += gc0 * pr.X2; gP[3] += gc0;
+            gP[4] += gc1 * pr.X0; gP[5] += gc1 * pr.X1; gP[6] += gc1 * pr.X2; gP[7] += gc1;
+            gP[8] += gc2 * pr.X0; gP[9] += gc2 * pr.X1; gP[10] += gc2 * pr.X2; gP[11] += gc2;
+        }
+    }
+
+    if (MODE == MODE_WARP && p.gP_partial) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int e = 0; e < 12; e++) {
+            const float v = warp_sum(gP[e]);
+            if (lane == 0) red[wid * 12 + e] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            float t = 0.f;
+            for (int w = 0; w < NT / 32; w++) t += red[w * 12 + threadIdx.x];
+            const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            p.gP_partial[cta * 12 + threadIdx.x] = t;
+        }
+    }
+}
+
+// ================================================================================================
+// Host launchers
+// ================================================================================================
+constexpr int F_TH = 16, F_TW = 64, F_NT = 256;
+constexpr int B_TH = 16, B_TW = 64, B_NT = 256;
+
+static inline dim3 tile_grid(int B, int H, int W, int TH, int TW)
+{
+    return dim3((W + TW - 1) / TW, (H + TH - 1) / TH, B);
+}
+
+static size_t partial_count(int B, int H, int W)
+{
+    const dim3 g = tile_grid(B, H, W, F_TH < B_TH ? F_TH : B_TH, F_TW < B_TW ? F_TW : B_TW);
+    return (size_t)g.x * g.y * g.z;
+}
+
+template <int MODE, int CK, bool NEED_GY>
+static constexpr size_t bwd_smem_bytes()
+{
+    return sizeof(float) * (2 * CK * (B_TH + 4) * (B_TW + 4) + CK * (NEED_GY ? 4 : 3) * (B_TH + 2) * (B_TW + 2) + 24 + (B_NT / 32) * 12);
+}
+
+template <int MODE, int CK, bool NEED_GY>
+static int launch_bwd(const WPParams &p, dim3 grid, cudaStream_t st)
+{
+    auto kern = warp_photo_bwd_kernel<MODE, CK, B_TH, B_TW, B_NT, NEED_GY>;
+    constexpr size_t smem = bwd_smem_bytes<MODE, CK, NEED_GY>();
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    kern<<<grid, B_NT, smem, st>>>(p);
+    count_launch();
+    return finish_launch("warp_photo_bwd_kernel");
+}
+
+static int fill_common(WPParams &p, int B, int C, int H, int W, int padding_mode, int use_mask, float eps, cudaStream_t st)
+{
+    E2E_REQUIRE(B > 0 && H >= 2 && W >= 2, "B=%d H=%d W=%d: need B>0, H>=2, W>=2 (reflection padding)", B, H, W);
+    E2E_REQUIRE(padding_mode == 0 || padding_mode == 1, "padding_mode must be 0 (zeros) or 1 (border)");
+    E2E_REQUIRE((long long)B * C <= 65535, "B*C exceeds gridDim.z");
+    p.B = B; p.C = C; p.H = H; p.W = W;
+    p.border = padding_mode; p.use_mask = use_mask; p.eps = eps;
+    p.wm1 = (float)(W - 1); p.hm1 = (float)(H - 1);
+    p.half_w = (float)W / 2; p.half_h = (float)H / 2;
+    p.dW = host_divc(p.wm1, st); p.dH = host_divc(p.hm1, st);
+    p.d9 = host_divc(9.0f, st); p.d3 = host_divc(3.0f, st);
+    return 0;
+}
+
+}  // namespace e2e
+
+using namespace e2e;
+
+extern "C" {
+
+size_t e2e_warp_photo_workspace_bytes(int B, int H, int W)
+{
+    // forward: one float per CTA; backward: 12 floats per CTA.  256-byte slack for alignment.
+    return partial_count(B, H, W) * 12 * sizeof(float) + 256;
+}
+
+int e2e_warp_photo_fwd(const float *depth, const float *inv_K, const float *K, const float *T,
+                       const float *src, const int64_t src_strides[4], const float *tgt, const int64_t tgt_strides[4],
+                       int B, int H, int W, int padding_mode, int use_mask, float eps,
+                       float *syn, float *valid, float *pix, float *loss_map, float *loss_mean,
+                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    WPParams p = {};
+    E2E_REQUIRE(depth && inv_K && K && T && src && tgt, "null input pointer");
+    if (int rc = fill_common(p, B, 3, H, W, padding_mode, use_mask, eps, st)) return rc;
+    p.depth = depth; p.inv_K = inv_K; p.K = K; p.T = T;
+    p.src = make_view(src, src_strides); p.tgt = make_view(tgt, tgt_strides);
+    p.syn = syn; p.valid = valid; p.pix = pix; p.loss_map = loss_map;
+    const dim3 grid = tile_grid(B, H, W, F_TH, F_TW);
+    const size_t nct = (size_t)grid.x * grid.y * grid.z;
+    if (loss_mean) {
+        E2E_REQUIRE(workspace && workspace_bytes >= nct * sizeof(float), "workspace too small for loss_mean");
+        p.partial = (float *)workspace;
+    }
+    warp_photo_fwd_kernel<MODE_WARP, 3, F_TH, F_TW, F_NT><<<grid, F_NT, 0, st>>>(p);
+    count_launch();
+    if (int rc = finish_launch("warp_photo_fwd_kernel")) return rc;
+    if (loss_mean) {
+        reduce_partials_kernel<<<1, 1024, 0, st>>>(p.partial, (long long)nct, 1.0 / ((double)B * H * W), loss_mean);
+        count_launch();
+        if (int rc = finish_launch("reduce_partials_kernel")) return rc;
+    }
+    return 0;
+}
+
+int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, const float *T,
+                       const float *src, const int64_t src_strides[4], const float *tgt, const int64_t tgt_strides[4],
+                       int B, int H, int W, int padding_mode, int use_mask, float eps,
+                       const float *grad_loss_map, const float *grad_scalar, float scalar_scale,
+                       float *grad_depth, float *grad_src, const int64_t grad_src_strides[4], float *grad_P,
+                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    WPParams p = {};
+    E2E_REQUIRE(depth && inv_K && K && T && src && tgt && grad_depth, "null pointer");
+    if (int rc = fill_common(p, B, 3, H, W, padding_mode, use_mask, eps, st)) return rc;
+    p.depth = depth; p.inv_K = inv_K; p.K = K; p.T = T;
+    p.src = make_view(src, src_strides); p.tgt = make_view(tgt, tgt_strides);
+    p.g_loss_map = grad_loss_map; p.g_scalar = grad_scalar; p.g_scale = scalar_scale;
+    p.g_depth = grad_depth;
+    if (grad_src) {
+        E2E_REQUIRE(grad_src_strides, "grad_src needs strides");
+        p.g_src = make_view_w(grad_src, grad_src_strides);
+    }
+    const dim3 grid = tile_grid(B, H, W, B_TH, B_TW);
+    const size_t nct = (size_t)grid.x * grid.y * grid.z;
+    if (grad_P) {
+        E2E_REQUIRE(workspace && workspace_bytes >= nct * 12 * sizeof(float), "workspace too small for grad_P");
+        p.gP_partial = (float *)workspace;
+    }
+    if (int rc = launch_bwd<MODE_WARP, 3, false>(p, grid, st)) return rc;
+    if (grad_P) {
+        reduce_gP_kernel<<<B * 12, 256, 0, st>>>(p.gP_partial, (int)(grid.x * grid.y), grad_P);
+        count_launch();
+        if (int rc = finish_launch("reduce_gP_kernel")) return rc;
+    }
+    return 0;
+}
+
+int e2e_ssim_fwd(const float *x, const int64_t x_strides[4], const float *y, const int64_t y_strides[4],
+                 int B, int C, int H, int W, float *ssim_map, float *loss_map, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    WPParams p = {};
+    E2E_REQUIRE(x && y && C >= 1, "null input / bad C");
+    E2E_REQUIRE(!loss_map || C == 3, "loss_map output requires C == 3 (photometric_loss, losses.py:97-117)");
+    if (int rc = fill_common(p, B, C, H, W, 1, 0, 0.f, st)) return rc;
+    p.src = make_view(x, x_strides); p.tgt = make_view(y, y_strides);
+    p.ssim = ssim_map; p.loss_map = loss_map;
+    dim3 grid = tile_grid(B, H, W, F_TH, F_TW);
+    if (C == 3) {
+        warp_photo_fwd_kernel<MODE_DIRECT, 3, F_TH, F_TW, F_NT><<<grid, F_NT, 0, st>>>(p);
+    } else {
+        grid.z = B * C;
+        warp_photo_fwd_kernel<MODE_DIRECT, 1, F_TH, F_TW, F_NT><<<grid, F_NT, 0, st>>>(p);
+    }
+    count_launch();
+    return finish_launch("ssim_fwd_kernel");
+}
+
+int e2e_ssim_bwd(const float *x, const int64_t x_strides[4], const float *y, const int64_t y_strides[4],
+                 int B, int C, int H, int W, const float *grad_ssim, const float *grad_loss_map,
+                 float *grad_x, float *grad_y, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    WPParams p = {};
+    E2E_REQUIRE(x && y && C >= 1 && (grad_ssim || grad_loss_map), "null input / no upstream gradient");
+    E2E_REQUIRE(!grad_loss_map || C == 3, "grad_loss_map requires C == 3");
+    if (int rc = fill_common(p, B, C, H, W, 1, 0, 0.f, st)) return rc;
+    p.src = make_view(x, x_strides); p.tgt = make_view(y, y_strides);
+    p.g_ssim = grad_ssim; p.g_loss_map = grad_loss_map;
+    p.g_x = grad_x; p.g_y = grad_y;
+    dim3 grid = tile_grid(B, H, W, B_TH, B_TW);
+    if (C == 3) return launch_bwd<MODE_DIRECT, 3, true>(p, grid, st);
+    grid.z = B * C;
+    return launch_bwd<MODE_DIRECT, 1, true>(p, grid, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,14 @@
+"""e2e_slam_b200 -- B200 (sm_100a) kernels for the differentiable-geometry hot path of
+End-To-End-Self-Supervised-SLAM, behind the reference's own Python call surface.
+
+Host-side mirror of the reference interface (same names, arguments and error behaviour):
+    view_synthesis.BackprojectDepth / Project3D        <- depth_estimation/view_synthesis.py
+    losses.SSIM / photometric_loss / ...               <- loss/losses.py
+    slam.PointFusion / RGBDImages / Pointclouds / ...  <- gradslam as used by slam/custom_slam.py
+    ops.warp_photometric / warp_photometric_loss       <- the fused tier
+The compute is in ../csrc (CUDA, C ABI in include/e2e_slam_b200.h); this package holds no fallback.
+"""
+from . import _lib  # noqa: F401
+from .ops import warp_photometric, warp_photometric_loss, ssim_map, photometric_map  # noqa: F401
+
+__all__ = ["warp_photometric", "warp_photometric_loss", "ssim_map", "photometric_map"]

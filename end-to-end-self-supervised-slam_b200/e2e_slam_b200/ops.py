@@ -1,0 +1,190 @@
+"""torch.autograd bindings of the fused CUDA kernels (tier (ii) of SURVEY.md section 8(b)).
+
+`warp_photometric` / `warp_photometric_loss` replace, for one source frame, the reference's
+    BackprojectDepth.forward -> Project3D.forward -> F.grid_sample -> mask multiply -> SSIM ->
+    photometric_loss (-> .mean())
+(train_depth.py:545-613 + 707-727; online_adaption.py:412-455 + 544-564) with one forward and one
+backward kernel.  Everything is fp32; all tensors must live on a CUDA device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, f32, lib, prepare_divisors, ptr, stream_ptr, strides4
+
+_PAD = {"zeros": 0, "border": 1}
+
+
+def _pad_code(padding_mode):
+    if padding_mode not in _PAD:
+        raise ValueError(f"padding_mode must be 'zeros' or 'border' (MODEL.padding_mode), got {padding_mode!r}")
+    return _PAD[padding_mode]
+
+
+def _mat44(m, B, name):
+    f32(m, name)
+    if m.dim() == 2:
+        m = m.unsqueeze(0)
+    if m.shape[-2:] != (4, 4):
+        raise ValueError(f"{name} must be (B,4,4), got {tuple(m.shape)}")
+    if m.shape[0] != B:
+        if m.shape[0] != 1:
+            raise ValueError(f"{name} batch {m.shape[0]} does not match depth batch {B}")
+        m = m.expand(B, 4, 4)
+    return m.contiguous()
+
+
+def _workspace(B, H, W, device):
+    n = lib().e2e_warp_photo_workspace_bytes(B, H, W)
+    return torch.empty(n, dtype=torch.uint8, device=device), n
+
+
+class _WarpPhotometric(torch.autograd.Function):
+    """mode 'map'  -> returns loss_map [B,1,H,W] (+ syn, valid, pix when materialise=True)
+       mode 'mean' -> returns the scalar mean of the loss map (lean path, nothing else is written)"""
+
+    @staticmethod
+    def forward(ctx, depth, inv_K, K, T, src, tgt, padding_mode, use_mask, eps, mode, materialise):
+        f32(depth, "depth"), f32(src, "source frame"), f32(tgt, "target frame")
+        if depth.dim() != 4 or depth.shape[1] != 1:
+            raise ValueError(f"depth must be (B,1,H,W), got {tuple(depth.shape)}")
+        B, _, H, W = depth.shape
+        if tuple(src.shape) != (B, 3, H, W) or tuple(tgt.shape) != (B, 3, H, W):
+            raise ValueError(f"source/target frames must be ({B},3,{H},{W}), got {tuple(src.shape)} / {tuple(tgt.shape)}")
+        depth_c = depth.contiguous()
+        inv_K_c, K_c, T_c = _mat44(inv_K, B, "inv_K"), _mat44(K, B, "K"), _mat44(T, B, "T")
+        prepare_divisors(W - 1, H - 1, 9.0, 3.0)
+        dev = depth.device
+        pad = _pad_code(padding_mode)
+        ws, ws_bytes = _workspace(B, H, W, dev)
+        syn = valid = pix = loss_map = loss_mean = None
+        if mode == "map":
+            loss_map = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+            if materialise:
+                syn = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+                valid = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+                pix = torch.empty(B, H, W, 2, dtype=torch.float32, device=dev)
+        else:
+            loss_mean = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib().e2e_warp_photo_fwd(ptr(depth_c), ptr(inv_K_c), ptr(K_c), ptr(T_c),
+                                          ptr(src), strides4(src), ptr(tgt), strides4(tgt),
+                                          B, H, W, pad, int(bool(use_mask)), ctypes.c_float(eps),
+                                          ptr(syn), ptr(valid), ptr(pix), ptr(loss_map), ptr(loss_mean),
+                                          ptr(ws), ws_bytes, stream_ptr())
+        check(rc, "e2e_warp_photo_fwd")
+        ctx.save_for_backward(depth_c, inv_K_c, K_c, T_c, src, tgt)
+        ctx.cfg = (B, H, W, pad, int(bool(use_mask)), float(eps), mode)
+        if mode == "map":
+            if materialise:
+                ctx.mark_non_differentiable(syn, valid, pix)
+                return loss_map, syn, valid, pix
+            return loss_map
+        return loss_mean.reshape(())
+
+    @staticmethod
+    def backward(ctx, *grads):
+        depth, inv_K, K, T, src, tgt = ctx.saved_tensors
+        B, H, W, pad, use_mask, eps, mode = ctx.cfg
+        g = grads[0]
+        dev = depth.device
+        need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
+        grad_depth = torch.empty_like(depth)
+        grad_src = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
+        grad_P = torch.empty(B, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
+        ws, ws_bytes = _workspace(B, H, W, dev)
+        if mode == "map":
+            g_map, g_scalar, scale = f32(g, "grad").contiguous(), None, 1.0
+        else:
+            g_map, g_scalar, scale = None, f32(g, "grad").reshape(1).contiguous(), 1.0 / (B * H * W)
+        with torch.cuda.device(dev):
+            rc = lib().e2e_warp_photo_bwd(ptr(depth), ptr(inv_K), ptr(K), ptr(T),
+                                          ptr(src), strides4(src), ptr(tgt), strides4(tgt),
+                                          B, H, W, pad, use_mask, ctypes.c_float(eps),
+                                          ptr(g_map), ptr(g_scalar), ctypes.c_float(scale),
+                                          ptr(grad_depth), ptr(grad_src),
+                                          strides4(grad_src) if grad_src is not None else None,
+                                          ptr(grad_P), ptr(ws), ws_bytes, stream_ptr())
+        check(rc, "e2e_warp_photo_bwd")
+        grad_K = grad_T = None
+        if grad_P is not None:
+            # P = (K @ T)[:3]  =>  dL/dT = K[:3]^T dL/dP ,  dL/dK[:3] = dL/dP T^T   (4x4 host-side plumbing)
+            if need_T:
+                grad_T = torch.matmul(K[:, :3, :].transpose(1, 2), grad_P)
+            if need_K:
+                grad_K = torch.zeros_like(K)
+                grad_K[:, :3, :] = torch.matmul(grad_P, T.transpose(1, 2))
+        return (grad_depth if need_depth else None, None, grad_K, grad_T, grad_src, None,
+                None, None, None, None, None)
+
+
+def warp_photometric(depth, inv_K, K, T, source_frame, target_frame, padding_mode="border",
+                     photometric_mask=True, need_outputs=False, eps=1e-7):
+    """Per-pixel photometric loss of warping `source_frame` into the target view.
+
+    Returns loss_map [B,1,H,W]; with need_outputs=True returns (loss_map, synthesized_frame [B,3,H,W],
+    valid_mask [B,1,H,W], pixel_coordinates [B,H,W,2]) -- the tensors the reference keeps in `outputs`
+    (train_depth.py:581-590).  Differentiable w.r.t. depth, K, T and source_frame."""
+    return _WarpPhotometric.apply(depth, inv_K, K, T, source_frame, target_frame, padding_mode,
+                                  photometric_mask, eps, "map", need_outputs)
+
+
+def warp_photometric_loss(depth, inv_K, K, T, source_frame, target_frame, padding_mode="border",
+                          photometric_mask=True, eps=1e-7):
+    """Scalar `photometric_loss(...).mean()` for one source frame (train_depth.py:657), lean path:
+    neither the synthesized frame nor the loss map is written to memory."""
+    return _WarpPhotometric.apply(depth, inv_K, K, T, source_frame, target_frame, padding_mode,
+                                  photometric_mask, eps, "mean", False)
+
+
+class _SSIM(torch.autograd.Function):
+    """mode 'ssim' -> SSIM map [B,C,H,W] (losses.py:23-37);  mode 'photo' -> loss map [B,1,H,W] (:97-117)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode):
+        f32(x, "x"), f32(y, "y")
+        if x.shape != y.shape or x.dim() != 4:
+            raise ValueError(f"x and y must be equal-shape (B,C,H,W) tensors, got {tuple(x.shape)} / {tuple(y.shape)}")
+        B, C, H, W = x.shape
+        prepare_divisors(9.0, 3.0, W - 1, H - 1)
+        dev = x.device
+        ssim_map = torch.empty(B, C, H, W, dtype=torch.float32, device=dev) if mode == "ssim" else None
+        loss_map = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev) if mode == "photo" else None
+        with torch.cuda.device(dev):
+            rc = lib().e2e_ssim_fwd(ptr(x), strides4(x), ptr(y), strides4(y), B, C, H, W,
+                                    ptr(ssim_map), ptr(loss_map), stream_ptr())
+        check(rc, "e2e_ssim_fwd")
+        ctx.save_for_backward(x, y)
+        ctx.mode = mode
+        return ssim_map if mode == "ssim" else loss_map
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dev = x.device
+        g = f32(g, "grad").contiguous()
+        gx = torch.empty(B, C, H, W, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        gy = torch.empty(B, C, H, W, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(dev):
+            rc = lib().e2e_ssim_bwd(ptr(x), strides4(x), ptr(y), strides4(y), B, C, H, W,
+                                    ptr(g if ctx.mode == "ssim" else None), ptr(g if ctx.mode == "photo" else None),
+                                    ptr(gx), ptr(gy), stream_ptr())
+        check(rc, "e2e_ssim_bwd")
+        return gx, gy, None
+
+
+def ssim_map(x, y):
+    return _SSIM.apply(x, y, "ssim")
+
+
+def photometric_map(prediction, target):
+    if prediction.dim() == 4 and prediction.shape[1] == 3:
+        return _SSIM.apply(prediction, target, "photo")
+    # other channel counts: SSIM kernel per plane, channel means are trivial torch reductions
+    return 0.85 * ssim_map(prediction, target).mean(1, True) + 0.15 * torch.abs(target - prediction).mean(1, True)
+
+
+def launch_count():
+    return _lib.launch_count()

@@ -1,0 +1,208 @@
+/*
+ * e2e_slam_b200 -- C ABI of the B200 (sm_100a) differentiable-geometry hot path.
+ *
+ * This is the drop-in boundary.  The reference
+ * (ivanalberico/End-To-End-Self-Supervised-SLAM) is 100 % Python and has no FFI of its own; the
+ * functions below are what a Python binding for each reference call site needs (ctypes stub in
+ * INTEGRATION.md; the shipped host-side mirror is end-to-end-self-supervised-slam_b200/e2e_slam_b200).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - fp32 everywhere (the reference never uses reduced precision), indices are int64 / int32 as stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous
+ *     and never synchronise, except e2e_prepare_divisor / e2e_fusion_count which say so;
+ *   - image tensors are addressed through element strides {batch, channel, row, col}, so the
+ *     reference's NCHW *views* of channels-last memory (train_depth.py:451-453) are consumed in place;
+ *   - the caller owns all memory; `workspace` buffers are caller-provided (size from the *_workspace_bytes
+ *     functions) and need no initialisation;
+ *   - return value 0 = success, otherwise a cudaError_t (or E2E_ERR_*) value; e2e_last_error() gives text.
+ *   - padding_mode: 0 = zeros, 1 = border (MODEL.padding_mode, configs/config.yaml:35).
+ */
+#ifndef E2E_SLAM_B200_H
+#define E2E_SLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2E_ERR_BAD_ARG 100001
+#define E2E_ERR_UNSUPPORTED 100002
+
+int e2e_abi_version(void);
+const char *e2e_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+unsigned long long e2e_launch_count(void);
+
+/* The reference divides by (W-1), (H-1), 9 and 3 with IEEE division.  The kernels replace x/d by a
+ * 3-instruction sequence that is correctly rounded for every x iff a property of d holds; this call
+ * checks that property exhaustively on the device (all 2^23 mantissas, ~20 us), caches the verdict and
+ * makes the kernels fall back to IEEE division for a divisor that fails.  Synchronises `stream` the
+ * first time a divisor is seen.  Returns 1 (fast path exact), 0 (IEEE fallback) or <0 on error. */
+int e2e_prepare_divisor(float d, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused inverse warp + photometric loss.  Replaces, in one forward and one backward kernel:
+ *   BackprojectDepth.forward   depth_estimation/view_synthesis.py:34-40
+ *   Project3D.forward          depth_estimation/view_synthesis.py:54-78 (geometric=False)
+ *   F.grid_sample              train_depth.py:587-590 / online_adaption.py:450-453 (align_corners=False)
+ *   mask multiply              train_depth.py:713-718
+ *   SSIM.forward               loss/losses.py:23-37
+ *   photometric_loss           loss/losses.py:97-117
+ *   .mean() over pixels        train_depth.py:657
+ * depth [B,1,H,W] contiguous; inv_K, K, T [B,4,4] row-major; src/tgt 3-channel images via strides.
+ * Optional outputs (NULL to skip): syn [B,3,H,W], valid [B,1,H,W], pix [B,H,W,2], loss_map [B,1,H,W],
+ * loss_mean [1] (mean of loss_map over B*H*W; needs workspace).
+ * --------------------------------------------------------------------------------------------- */
+size_t e2e_warp_photo_workspace_bytes(int B, int H, int W);
+
+int e2e_warp_photo_fwd(const float *depth, const float *inv_K, const float *K, const float *T,
+                       const float *src, const int64_t src_strides[4],
+                       const float *tgt, const int64_t tgt_strides[4],
+                       int B, int H, int W, int padding_mode, int use_mask, float eps,
+                       float *syn, float *valid, float *pix, float *loss_map, float *loss_mean,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Upstream gradient: grad_loss_map [B,1,H,W] if non-NULL, else the scalar (*grad_scalar) * scalar_scale
+ * for every pixel (grad_scalar is a device pointer; NULL means 1.0).  Outputs: grad_depth [B,1,H,W]
+ * (written), grad_src (ACCUMULATED with atomics into a caller-zeroed buffer addressed by
+ * grad_src_strides; NULL to skip), grad_P [B,3,4] = dL/d((K@T)[:3]) (written, deterministic two-pass
+ * reduction; NULL to skip).  The host maps grad_P to grad_T = K[:3]^T grad_P, grad_K[:3] = grad_P T^T. */
+int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, const float *T,
+                       const float *src, const int64_t src_strides[4],
+                       const float *tgt, const int64_t tgt_strides[4],
+                       int B, int H, int W, int padding_mode, int use_mask, float eps,
+                       const float *grad_loss_map, const float *grad_scalar, float scalar_scale,
+                       float *grad_depth, float *grad_src, const int64_t grad_src_strides[4], float *grad_P,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone SSIM / photometric loss on given images (tier (i) drop-in for loss/losses.py:6-37 and
+ * :97-117, also used for the auto-masking variant train_depth.py:729-750).  x, y are [B,C,H,W] via
+ * strides.  ssim_map [B,C,H,W] and/or loss_map [B,1,H,W] (loss_map requires C == 3) may be NULL.
+ * Backward: upstream grad_ssim [B,C,H,W] and/or grad_loss_map [B,1,H,W]; outputs grad_x, grad_y
+ * [B,C,H,W] contiguous (either may be NULL).
+ * --------------------------------------------------------------------------------------------- */
+int e2e_ssim_fwd(const float *x, const int64_t x_strides[4], const float *y, const int64_t y_strides[4],
+                 int B, int C, int H, int W, float *ssim_map, float *loss_map, void *stream);
+
+int e2e_ssim_bwd(const float *x, const int64_t x_strides[4], const float *y, const int64_t y_strides[4],
+                 int B, int C, int H, int W, const float *grad_ssim, const float *grad_loss_map,
+                 float *grad_x, float *grad_y, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Granular view-synthesis ops (tier (i): one kernel per reference call, same tensors in and out).
+ *   e2e_backproject_*  BackprojectDepth.forward, view_synthesis.py:34-40 -> cam_points [B,4,H*W]
+ *   e2e_project3d_*    Project3D.forward, view_synthesis.py:54-78 -> pix [B,H,W,2], valid [B,1,H,W],
+ *                      warped_depth [B,1,H,W] (geometric=True, :73-76; NULL to skip)
+ *   e2e_grid_sample_*  F.grid_sample bilinear, padding zeros|border, align_corners 0|1
+ *                      (train_depth.py:568-590); input [B,C,H,W] via strides, grid [B,Ho,Wo,2] contiguous
+ * --------------------------------------------------------------------------------------------- */
+int e2e_backproject_fwd(const float *depth, const float *inv_K, int B, int H, int W, float *cam_points, void *stream);
+int e2e_backproject_bwd(const float *grad_cam, const float *inv_K, int B, int H, int W, float *grad_depth, void *stream);
+
+int e2e_project3d_fwd(const float *points, const float *K, const float *T, int B, int H, int W, float eps,
+                      float *pix, float *valid, float *warped_depth, void *stream);
+/* grad_points [B,4,H*W] written; grad_P [B,3,4] written (NULL to skip; needs workspace). */
+int e2e_project3d_bwd(const float *points, const float *K, const float *T, int B, int H, int W, float eps,
+                      const float *grad_pix, const float *grad_warped_depth,
+                      float *grad_points, float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
+
+int e2e_grid_sample_fwd(const float *input, const int64_t in_strides[4], const float *grid,
+                        int B, int C, int H, int W, int Ho, int Wo, int padding_mode, int align_corners,
+                        float *output, void *stream);
+/* grad_input is ACCUMULATED (caller zeroes it) through grad_in_strides; grad_grid [B,Ho,Wo,2] written. */
+int e2e_grid_sample_bwd(const float *grad_output, const float *input, const int64_t in_strides[4],
+                        const float *grid, int B, int C, int H, int W, int Ho, int Wo,
+                        int padding_mode, int align_corners,
+                        float *grad_input, const int64_t grad_in_strides[4], float *grad_grid, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small fused losses.
+ *   e2e_smooth_*     compute_smoothness_loss (train_depth.py:763-773) + disparity_smoothness_loss
+ *                    (loss/losses.py:119-132): per-image mean normalisation, edge-aware |dx|,|dy|, two means.
+ *                    disp [B,1,H,W] contiguous, img 3-channel via strides.  loss [1].
+ *   e2e_sparse_l1_*  depth_gt_loss (loss/losses.py:151-160): mean over all n elements of |pred*mask - gt|.
+ *   e2e_depth_reg_*  depth_reguralizer (loss/losses.py:134-148): kind 1 = L1, 2 = L2 (MSE).
+ *   e2e_geometric_fwd geometric_consistency_loss (loss/losses.py:84-95), forward only; the >10000
+ *                    mask-count test is evaluated on the device (no host sync).
+ * Backward entry points take the upstream scalar gradient as a device pointer (NULL = 1.0).
+ * --------------------------------------------------------------------------------------------- */
+size_t e2e_reduce_workspace_bytes(long long n_elements);
+
+int e2e_smooth_fwd(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
+                   float *loss, void *workspace, size_t workspace_bytes, void *stream);
+int e2e_smooth_bwd(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
+                   const float *grad_loss, float *grad_disp, void *workspace, size_t workspace_bytes, void *stream);
+
+int e2e_sparse_l1_fwd(const float *pred, const float *mask, const float *gt, long long n, float *loss,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int e2e_sparse_l1_bwd(const float *pred, const float *mask, const float *gt, long long n,
+                      const float *grad_loss, float *grad_pred, void *stream);
+
+int e2e_depth_reg_fwd(const float *initial, const float *refined, long long n, int kind, float *loss,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int e2e_depth_reg_bwd(const float *initial, const float *refined, long long n, int kind,
+                      const float *grad_loss, float *grad_refined, void *stream);
+
+int e2e_geometric_fwd(const float *warped_depth, const float *interp_depth, const float *valid, long long n,
+                      float *loss, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PointFusion (gradslam semantics; gradslam itself is not vendored by the
+ * reference -- call sites slam/custom_slam.py:33, online_adaption.py:354-363, 466-469, train_depth.py:266).
+ * Map layout: structure of arrays, points/normals/colors [cap,3] fp32, ccount [cap] fp32.
+ *
+ *   e2e_rgbd_maps         RGBDImages.vertex_map / normal_map / global_* / valid mask + PointFusion alpha for
+ *                         one frame: depth [H,W], rgb [H,W,3], intrinsics K [4,4], pose [4,4] (camera->world).
+ *                         Outputs vertex_g, normal_g [H,W,3], alpha [H,W], valid [H,W] (uint8).
+ *   e2e_fusion_associate  find_active_map_points + find_similar_map_points + find_best_unique_correspondences:
+ *                         writes index_map [H,W] int64 (map point matched to each live pixel, -1 = none).
+ *                         `keys` is an [H,W] uint64 scratch image.
+ *   e2e_fusion_merge_append fuse_with_map: confidence-weighted merge of matched map points in place, then
+ *                         stream-compacted append (row-major pixel order) of valid unmatched live pixels at
+ *                         map[n_map ...].  `n_out` (device int64[1]) receives the new point count;
+ *                         `append_slot` [H,W] int64 receives, per pixel, the slot it was appended to (-1 = not
+ *                         appended) so the backward can route gradients.  Capacity must be >= n_map + H*W.
+ * --------------------------------------------------------------------------------------------- */
+int e2e_rgbd_maps(const float *depth, const float *rgb, const float *K, const float *pose, int H, int W, float sigma,
+                  float *vertex_g, float *normal_g, float *alpha, unsigned char *valid, void *stream);
+
+int e2e_rgbd_maps_bwd(const float *depth, const float *K, const float *pose, int H, int W, float sigma,
+                      const float *grad_vertex_g, const float *grad_normal_g, const float *grad_alpha,
+                      float *grad_depth, void *stream);
+
+int e2e_fusion_associate(const float *map_points, const float *map_normals, const float *map_ccount, long long n_map,
+                         const float *K, const float *pose, const float *vertex_g, const float *normal_g,
+                         const unsigned char *valid, int H, int W, float dist_th, float dot_th,
+                         unsigned long long *keys, long long *index_map, void *stream);
+
+size_t e2e_fusion_workspace_bytes(int H, int W);
+
+int e2e_fusion_merge_append(float *map_points, float *map_normals, float *map_colors, float *map_ccount,
+                            long long n_map, long long capacity,
+                            const float *vertex_g, const float *normal_g, const float *rgb, const float *alpha,
+                            const unsigned char *valid, const long long *index_map, int H, int W,
+                            long long *append_slot, long long *n_out,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K = 1 nearest neighbour (chamferdist.chamfer.knn_points as used by knn_points_loss,
+ * loss/losses.py:39-63, and compute_3d_loss, online_adaption.py:638-645).
+ * query [P1,3] (optionally transformed on load by a row-major 4x4 `transform`, which is
+ * gradslam.geometry.geometryutils.transform_pointcloud fused in), ref [P2,3].
+ * Outputs dist2 [P1] (squared L2) and idx [P1] int64 (lowest index among exact ties).
+ * Backward: grad_query[i] = 2*(q_i - r_idx[i])*g_i written (in the un-transformed frame when a
+ * transform is given); grad_ref accumulated with atomics (NULL to skip).
+ * --------------------------------------------------------------------------------------------- */
+int e2e_knn1_fwd(const float *query, const float *transform, const float *ref, long long P1, long long P2,
+                 float *dist2, long long *idx, void *stream);
+int e2e_knn1_bwd(const float *query, const float *transform, const float *ref, long long P1, long long P2,
+                 const long long *idx, const float *grad_dist2, float *grad_query, float *grad_ref, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2E_SLAM_B200_H */
