@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 differentiable-geometry hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): warped px/s of the fused inverse warp + SSIM/L1 photometric loss, forward +
+backward (gradients to depth, pose and source image).  Workload = BASELINE config "C4 batched-256":
+256 synthetic ICL-shaped 480x640 key-frame pairs per GPU, S = 1 source frame, border padding,
+photometric mask on.  One step = one forward + backward pass over the batch.
+Multi-GPU: pairs are independent, every rank owns its own 256 pairs (weak scaling, no data-path
+collective); at N > 1 each step also all-reduces a 57.3 MB fp32 bucket -- the size of the depth network's
+adaptation gradients -- over NCCL, overlapped on a side stream.
+
+Output: ONE JSON line on rank 0 (contract in the task statement), including
+  value      device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
+  e2e        same metric through the public Python API with HOST inputs: pinned H2D copies + loss D2H inside
+  roofline   dominant kernel (backward) algorithmic bytes / event-timed duration vs measured HBM peak
+  cpu_baseline  the reference's CPU path (torch-op oracle) on a bounded sample, on this box's host cores
+  fusion     secondary metric "points fused/s" of PointFusion over a 60-frame sequence (config C3)
+`--impl reference` times the reference's own CPU implementation of the path (the torch-op restatement in
+oracle/torch_oracle.py, bit-identical to the reference on CPU) with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "end-to-end-self-supervised-slam_b200"))
+
+import torch  # noqa: E402
+
+H, W = 480, 640
+GRAD_BUCKET_ELEMS = 14_319_409          # DispResNet_Indoor(18) trainable values in refinement mode
+ALG_BYTES_FWD = 16 + 12                 # per target pixel, S = 1: depth 4 + target 12 + source 12
+ALG_BYTES_BWD = 20 + 24                 # re-read 28 + grad_depth 4 + grad_src 12
+METRIC = "warped px/s (fwd+bwd photometric loss)"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def cpu_reference_px_per_s(pairs, reps, warm, threads):
+    """The reference's CPU path (torch-op restatement, same ATen kernels the reference runs) fwd+bwd."""
+    from e2e_slam_b200.synthetic import make_pairs
+    from oracle import torch_oracle
+    torch.set_num_threads(threads)
+    d = make_pairs(pairs, H, W, "icl", seed=1234)
+    src, tgt = d["colors"][:, 0], d["colors"][:, 1]
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        torch_oracle.fwd_bwd(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt, "border", True)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return pairs * H * W / min(times), pairs * H * W / (sum(times) / len(times)), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pairs = args.cpu_pairs
+    from e2e_slam_b200.synthetic import make_pairs
+    from oracle import torch_oracle
+    torch.set_num_threads(threads)
+    d = make_pairs(pairs, H, W, "icl", seed=1234)
+    src, tgt = d["colors"][:, 0], d["colors"][:, 1]
+    step = lambda: torch_oracle.fwd_bwd(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt, "border", True)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = pairs * H * W * args.steps / dt
+    sample = f"{pairs} of the workload's 256 pairs per step, 480x640, fwd+bwd (grads to depth, source, pose), fp32, {threads} torch threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "px/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 batched-256 (bounded sample on CPU)", "pairs_per_step": pairs, "height": H, "width": W,
+                   "source_frames": 1, "padding_mode": "border", "photometric_mask": True},
+        "cpu_baseline": {"value": v, "unit": "px/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import e2e_slam_b200 as e2e
+    from e2e_slam_b200 import ops
+    from e2e_slam_b200.synthetic import make_pairs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P = args.pairs_per_gpu
+
+    # ---- synthetic inputs, resident in HBM (2.2 GB per GPU >> 126 MB L2) ------------------------------
+    chunks = [make_pairs(min(32, P - s), H, W, "icl", seed=1000 * rank + s, device=dev) for s in range(0, P, 32)]
+    d = {k: torch.cat([c[k] for c in chunks]) for k in chunks[0]}
+    del chunks
+    src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)   # NCHW views of NHWC memory
+    plan = ops.WarpPhotoPlan(P, H, W, dev)
+    bucket = torch.zeros(GRAD_BUCKET_ELEMS, device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    fwd_ms, bwd_ms = [], []
+
+    def step(record):
+        if world > 1:   # depth-net gradient bucket all-reduce, overlapped with this step's kernels
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                work = dist.all_reduce(bucket, async_op=True)
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        loss = plan.forward(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+        e1.record()
+        plan.grad_src.zero_()
+        e2.record()
+        lib_bwd()
+        e3.record()
+        if world > 1:
+            work.wait()
+            torch.cuda.current_stream().wait_stream(comm)
+        if record is not None:
+            record.append((e0, e1, e2, e3))
+        return loss
+
+    def lib_bwd():
+        # WarpPhotoPlan.backward minus the zero_() (timed separately above)
+        import ctypes
+        from e2e_slam_b200._lib import check, lib, ptr, stream_ptr, strides4
+        rc = lib().e2e_warp_photo_bwd(ptr(d["depth"]), ptr(d["inv_K"]), ptr(d["K"]), ptr(d["T"]), ptr(src), strides4(src),
+                                      ptr(tgt), strides4(tgt), P, H, W, plan.pad, plan.mask, ctypes.c_float(plan.eps),
+                                      None, None, ctypes.c_float(1.0 / (P * H * W)), ptr(plan.grad_depth),
+                                      ptr(plan.grad_src), plan._gs_strides, ptr(plan.grad_P), ptr(plan.ws), plan.ws_bytes,
+                                      stream_ptr())
+        check(rc, "e2e_warp_photo_bwd")
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(None)
+    sync_all()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.launch_count()
+    recs = []
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    for _ in range(args.steps):
+        loss = step(recs)
+    t_end.record()
+    sync_all()
+    launches = ops.launch_count() - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    for e0, e1, e2, e3 in recs:
+        fwd_ms.append(e0.elapsed_time(e1))
+        bwd_ms.append(e2.elapsed_time(e3))
+    clk = clocks.stop() if clocks else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t)
+    px_per_step = P * H * W * world
+    value = px_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API: host inputs, pinned H2D inside the timed region ----------
+    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in d.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def e2e_step():
+        dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        depth = dd["depth"].requires_grad_(True)
+        colors = dd["colors"].requires_grad_(True)       # gradient to the source image, as in `value`
+        T = dd["T"].requires_grad_(True)                 # gradient to the pose
+        s, t_ = colors[:, 0].permute(0, 3, 1, 2), colors[:, 1].permute(0, 3, 1, 2)
+        l = e2e.warp_photometric_loss(depth, dd["inv_K"], dd["K"], T, s, t_, "border", True)
+        l.backward()
+        return float(l.item())                           # 4-byte D2H read of the result
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        lval = e2e_step()
+    sync_all()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t)
+    e2e_value = px_per_step * e2e_steps / e2e_dt
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (backward) and friends ------------------------------------------
+    peak, peak_src = measured_peak()
+    bwd_avg, fwd_avg = sum(bwd_ms) / len(bwd_ms), sum(fwd_ms) / len(fwd_ms)
+    npx = P * H * W
+    ach_b = ALG_BYTES_BWD * npx / (bwd_avg * 1e-3) / 1e9
+    ach_f = ALG_BYTES_FWD * npx / (fwd_avg * 1e-3) / 1e9
+    traffic = ncu_traffic() or {}
+    roof = {"bound": "hbm", "kernel": "warp_photo_bwd_kernel (+ grad_P reduce)", "achieved": ach_b, "peak": peak, "unit": "GB/s",
+            "frac": ach_b / peak, "traffic": traffic.get("bwd_bytes_per_launch"), "peak_source": peak_src,
+            "algorithmic_bytes_per_px": ALG_BYTES_BWD, "ms_per_launch": bwd_avg}
+    roof_f = {"bound": "hbm", "kernel": "warp_photo_fwd_kernel (+ partial-sum reduce)", "achieved": ach_f, "peak": peak, "unit": "GB/s",
+              "frac": ach_f / peak, "traffic": traffic.get("fwd_bytes_per_launch"), "algorithmic_bytes_per_px": ALG_BYTES_FWD,
+              "ms_per_launch": fwd_avg}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------------------------
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        best, mean, times = cpu_reference_px_per_s(args.cpu_pairs, reps=3, warm=1, threads=threads)
+        cpu = {"value": best, "unit": "px/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_pairs} of the 256 pairs, 480x640, fwd+bwd, torch-op restatement of the reference "
+                         f"(oracle/torch_oracle.py), best of 3 after 1 warm-up, {threads} threads"}
+
+    # ---- secondary metric: PointFusion points fused/s (config C3) ----------------------------------------
+    fusion = None
+    if world == 1 and not args.skip_fusion:
+        try:
+            from e2e_slam_b200 import fusion_bench
+            fusion = fusion_bench.run(dev)
+        except ImportError:
+            fusion = None
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 batched-256: 256 ICL-shaped 480x640 key-frame pairs per GPU, S=1, fused warp+SSIM/L1 fwd+bwd "
+                               "(grads to depth, source image, pose)", "pairs_per_gpu": P, "global_pairs": P * world,
+                   "height": H, "width": W, "source_frames": 1, "padding_mode": "border", "photometric_mask": True,
+                   "l2_policy": "inputs (2.2 GB/GPU) larger than L2; no explicit flush",
+                   "collective": None if world == 1 else f"NCCL all-reduce of {GRAD_BUCKET_ELEMS} fp32 depth-net gradients per step, overlapped"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+                "steps": e2e_steps, "loss": lval},
+        "gpu_launches": launches,
+        "roofline": roof, "roofline_fwd": roof_f,
+        "roofline_step": {"achieved": (ALG_BYTES_FWD + ALG_BYTES_BWD) * npx / ((fwd_avg + bwd_avg) * 1e-3) / 1e9, "peak": peak,
+                          "frac": (ALG_BYTES_FWD + ALG_BYTES_BWD) * npx / ((fwd_avg + bwd_avg) * 1e-3) / 1e9 / peak,
+                          "algorithmic_bytes_per_px": ALG_BYTES_FWD + ALG_BYTES_BWD},
+        "cpu_baseline": cpu, "fusion": fusion, "loss": float(loss),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=256)
+    ap.add_argument("--cpu-pairs", type=int, default=16)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-fusion", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

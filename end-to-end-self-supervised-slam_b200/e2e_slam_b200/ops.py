@@ -188,3 +188,51 @@ def photometric_map(prediction, target):
 
 def launch_count():
     return _lib.launch_count()
+
+
+class WarpPhotoPlan:
+    """Pre-allocated, autograd-free driver of the fused kernels for a fixed (B, H, W): the form a training
+    loop (or a CUDA graph) wants -- no allocation, no host synchronisation, two kernel launches forward
+    (fused kernel + partial-sum reduce) and two backward (fused kernel + grad_P reduce).
+
+        plan = WarpPhotoPlan(B, H, W, device)
+        loss = plan.forward(depth, inv_K, K, T, src, tgt)              # device scalar: mean photometric loss
+        g_depth, g_src, g_P = plan.backward(depth, inv_K, K, T, src, tgt)   # d loss / d {depth, src, (K@T)[:3]}
+    """
+
+    def __init__(self, B, H, W, device, padding_mode="border", photometric_mask=True, eps=1e-7,
+                 need_src_grad=True, need_pose_grad=True):
+        self.B, self.H, self.W = B, H, W
+        self.device = torch.device(device)
+        self.pad, self.mask, self.eps = _pad_code(padding_mode), int(bool(photometric_mask)), float(eps)
+        with torch.cuda.device(self.device):
+            prepare_divisors(W - 1, H - 1, 9.0, 3.0)
+        self.ws, self.ws_bytes = _workspace(B, H, W, self.device)
+        f = dict(dtype=torch.float32, device=self.device)
+        self.loss = torch.empty(1, **f)
+        self.grad_depth = torch.empty(B, 1, H, W, **f)
+        self.grad_src = torch.empty(B, 3, H, W, **f) if need_src_grad else None
+        self.grad_P = torch.empty(B, 3, 4, **f) if need_pose_grad else None
+        self._gs_strides = strides4(self.grad_src) if need_src_grad else None
+
+    def forward(self, depth, inv_K, K, T, src, tgt):
+        with torch.cuda.device(self.device):
+            rc = lib().e2e_warp_photo_fwd(ptr(depth), ptr(inv_K), ptr(K), ptr(T), ptr(src), strides4(src),
+                                          ptr(tgt), strides4(tgt), self.B, self.H, self.W, self.pad, self.mask,
+                                          ctypes.c_float(self.eps), None, None, None, None, ptr(self.loss),
+                                          ptr(self.ws), self.ws_bytes, stream_ptr())
+        check(rc, "e2e_warp_photo_fwd")
+        return self.loss
+
+    def backward(self, depth, inv_K, K, T, src, tgt, grad_loss=None):
+        if self.grad_src is not None:
+            self.grad_src.zero_()          # the kernel accumulates into it with red.global.add
+        with torch.cuda.device(self.device):
+            rc = lib().e2e_warp_photo_bwd(ptr(depth), ptr(inv_K), ptr(K), ptr(T), ptr(src), strides4(src),
+                                          ptr(tgt), strides4(tgt), self.B, self.H, self.W, self.pad, self.mask,
+                                          ctypes.c_float(self.eps), None, ptr(grad_loss),
+                                          ctypes.c_float(1.0 / (self.B * self.H * self.W)),
+                                          ptr(self.grad_depth), ptr(self.grad_src), self._gs_strides,
+                                          ptr(self.grad_P), ptr(self.ws), self.ws_bytes, stream_ptr())
+        check(rc, "e2e_warp_photo_bwd")
+        return self.grad_depth, self.grad_src, self.grad_P
