@@ -14,6 +14,14 @@
 //
 // Forward arithmetic follows oracle/warp_photo_oracle.c operation for operation, which reproduces the
 // reference (view_synthesis.py:34-78, F.grid_sample, losses.py:23-37, 111-115) bit for bit.
+//
+// Division strategy.  The reference divides by 9 (avg_pool2d), 3 (channel mean) and W-1 / H-1 with IEEE
+// division.  x/d is evaluated as q = x*c, r = fma(-d,q,x), q' = fma(r,c,q) (c = RN(1/d)), which equals
+// RN(x/d) for every x with |x| in [2^-122, 2^127) or x == 0 once d has passed the exhaustive mantissa
+// check (e2e_prepare_divisor).  Instead of guarding each of the ~20 divisions per pixel, phase 1 checks
+// the VALUES it stores (each must be 0 or have 2^-40 <= |v| <= 2^40, which bounds every window sum and
+// product away from the failing range) and the CTA votes once; a CTA that sees anything else (denormal
+// garbage, inf, NaN) takes the IEEE-division code path.  Either way the result is the reference's bits.
 #include "common.cuh"
 
 namespace e2e {
@@ -28,9 +36,9 @@ struct WPParams {
     const float *depth, *inv_K, *K, *T;
     ImgView src, tgt;          // WARP: source / target image.  DIRECT: x / y.
     int B, C, H, W;            // C = channels of the tensors (DIRECT may be != 3; kernel planes = B*C/CK)
-    int border, use_mask;
+    int border, use_mask, div_exact;
     float eps, wm1, hm1, half_w, half_h;
-    DivC dW, dH, d9, d3;
+    float rcpW, rcpH;          // RN(1/(W-1)), RN(1/(H-1))
     // forward outputs (nullable)
     float *syn, *valid, *pix, *ssim, *loss_map, *partial;
     // backward
@@ -41,6 +49,46 @@ struct WPParams {
     float *gP_partial;
     float *g_x, *g_y;
 };
+
+// Per-CTA image handle: batch offset applied, 32-bit element strides (host checks they fit).
+struct Img32 {
+    const float *p;
+    int sc, sh, sw;
+};
+
+__device__ __forceinline__ Img32 cta_image(const ImgView &v, int b)
+{
+    return Img32{v.p + (long long)b * v.sb, (int)v.sc, (int)v.sh, (int)v.sw};
+}
+
+// ------------------------------------------------------------------------------------------------
+// Division helpers (see header comment).
+// ------------------------------------------------------------------------------------------------
+template <bool IEEE>
+__device__ __forceinline__ float div_const(float x, float d, float rcp)
+{
+    if (IEEE) return __fdiv_rn(x, d);
+    const float q = __fmul_rn(x, rcp);
+    const float r = __fmaf_rn(-d, q, x);
+    return __fmaf_rn(r, rcp, q);
+}
+
+// u / d for a pixel coordinate u (d = W-1 or H-1 > 0).  |u| below 2^-122 needs no care: the caller
+// computes (q - 0.5) * 2, which is -1 for any such q.  +-inf (z' == 0) must stay +-inf.
+__device__ __forceinline__ float div_coord(float u, float d, float rcp, int exact)
+{
+    if (!exact) return __fdiv_rn(u, d);           // uniform branch: divisor failed the mantissa check
+    const float q = __fmul_rn(u, rcp);
+    const float r = __fmaf_rn(-d, q, u);
+    const float q2 = __fmaf_rn(r, rcp, q);
+    return (fabsf(u) == INFINITY) ? q : q2;
+}
+
+__device__ __forceinline__ bool value_out_of_fast_range(float v)
+{
+    const float a = fabsf(v);
+    return !((a >= 0x1p-40f && a <= 0x1p40f) || a == 0.0f);    // NaN -> true
+}
 
 // ------------------------------------------------------------------------------------------------
 // Camera constants of one batch element, staged once per CTA: cam[0..8] = inv_K[:3,:3],
@@ -68,7 +116,17 @@ struct Proj {
     float gx, gy, valid;   // normalised grid coordinate, validity
 };
 
-__device__ __forceinline__ void project_pixel(const float *cam, const WPParams &p, int x, int y, float d, Proj &o)
+struct PixConst {          // per-thread copies of the hot scalars (keeps them out of the constant bank)
+    float eps, wm1, hm1, half_w, half_h, rcpW, rcpH;
+    int border, exact;
+};
+
+__device__ __forceinline__ PixConst pix_const(const WPParams &p)
+{
+    return PixConst{p.eps, p.wm1, p.hm1, p.half_w, p.half_h, p.rcpW, p.rcpH, p.border, p.div_exact};
+}
+
+__device__ __forceinline__ void project_pixel(const float *cam, const PixConst &k, int x, int y, float d, Proj &o)
 {
     const float fx = (float)x, fy = (float)y;
     // sgemm k-loop (k = 0,1,2) then * depth               view_synthesis.py:36-38
@@ -82,10 +140,10 @@ __device__ __forceinline__ void project_pixel(const float *cam, const WPParams &
     o.c0 = xadd(xfma(P[2], o.X2, xfma(P[1], o.X1, xmul(P[0], o.X0))), P[3]);
     o.c1 = xadd(xfma(P[6], o.X2, xfma(P[5], o.X1, xmul(P[4], o.X0))), P[7]);
     o.c2 = xadd(xfma(P[10], o.X2, xfma(P[9], o.X1, xmul(P[8], o.X0))), P[11]);
-    o.z = xadd(o.c2, p.eps);                               // :60
+    o.z = xadd(o.c2, k.eps);                               // :60
     const float u = xdiv(o.c0, o.z), v = xdiv(o.c1, o.z);
-    o.gx = xmul(xsub(xdivc(u, p.dW), 0.5f), 2.0f);         // :66-68
-    o.gy = xmul(xsub(xdivc(v, p.dH), 0.5f), 2.0f);
+    o.gx = xmul(xsub(div_coord(u, k.wm1, k.rcpW, k.exact), 0.5f), 2.0f);   // :66-68
+    o.gy = xmul(xsub(div_coord(v, k.hm1, k.rcpH, k.exact), 0.5f), 2.0f);
     o.valid = (fabsf(o.gx) <= 1.0f && fabsf(o.gy) <= 1.0f) ? 1.0f : 0.0f;   // :70-71 (NaN -> 0)
 }
 
@@ -94,21 +152,21 @@ struct Samp {
     float ix, iy;              // after padding handling
     float nw, ne, sw, se;      // weights of taps (y0,x0) (y0,x1) (y1,x0) (y1,x1)
     int x0, y0;
-    bool inx0, inx1, iny0, iny1;
+    bool in00, in01, in10, in11;   // tap (row, col) in bounds: in<row><col>
     float mx, my;              // d(clamped)/d(unclamped): 0 where the border clamp is active
 };
 
-__device__ __forceinline__ void sampler_setup(const WPParams &p, float gx, float gy, Samp &s)
+__device__ __forceinline__ void sampler_setup(const PixConst &k, float gx, float gy, Samp &s)
 {
-    float ix = xfma(xadd(gx, 1.0f), p.half_w, -0.5f);
-    float iy = xfma(xadd(gy, 1.0f), p.half_h, -0.5f);
+    float ix = xfma(xadd(gx, 1.0f), k.half_w, -0.5f);
+    float iy = xfma(xadd(gy, 1.0f), k.half_h, -0.5f);
     s.mx = 1.0f;
     s.my = 1.0f;
-    if (p.border) {
-        s.mx = (ix > 0.0f && ix < p.wm1) ? 1.0f : 0.0f;    // clip_coordinates_set_grad
-        s.my = (iy > 0.0f && iy < p.hm1) ? 1.0f : 0.0f;
-        ix = fminf(p.wm1, fmaxf(0.0f, ix));                // NaN clamps to 0
-        iy = fminf(p.hm1, fmaxf(0.0f, iy));
+    if (k.border) {
+        s.mx = (ix > 0.0f && ix < k.wm1) ? 1.0f : 0.0f;    // clip_coordinates_set_grad
+        s.my = (iy > 0.0f && iy < k.hm1) ? 1.0f : 0.0f;
+        ix = fminf(k.wm1, fmaxf(0.0f, ix));                // NaN clamps to 0
+        iy = fminf(k.hm1, fmaxf(0.0f, iy));
     }
     const float xw = floorf(ix), yn = floorf(iy);
     const float w = xsub(ix, xw), e = xsub(1.0f, w), n = xsub(iy, yn), so = xsub(1.0f, n);
@@ -119,23 +177,33 @@ __device__ __forceinline__ void sampler_setup(const WPParams &p, float gx, float
     s.ix = ix;
     s.iy = iy;
     // float comparisons so that NaN / huge coordinates are simply out of bounds
-    s.inx0 = (xw >= 0.0f) && (xw <= p.wm1);
-    s.inx1 = (xw >= -1.0f) && (xw <= p.wm1 - 1.0f);
-    s.iny0 = (yn >= 0.0f) && (yn <= p.hm1);
-    s.iny1 = (yn >= -1.0f) && (yn <= p.hm1 - 1.0f);
-    s.x0 = (s.inx0 || s.inx1) ? (int)xw : 0;
-    s.y0 = (s.iny0 || s.iny1) ? (int)yn : 0;
+    const bool inx0 = (xw >= 0.0f) && (xw <= k.wm1), inx1 = (xw >= -1.0f) && (xw <= k.wm1 - 1.0f);
+    const bool iny0 = (yn >= 0.0f) && (yn <= k.hm1), iny1 = (yn >= -1.0f) && (yn <= k.hm1 - 1.0f);
+    s.in00 = iny0 && inx0;
+    s.in01 = iny0 && inx1;
+    s.in10 = iny1 && inx0;
+    s.in11 = iny1 && inx1;
+    s.x0 = (inx0 || inx1) ? (int)xw : 0;
+    s.y0 = (iny0 || iny1) ? (int)yn : 0;
 }
 
-__device__ __forceinline__ void gather_taps(const ImgView &im, int b, const Samp &s, int ch, float v[4])
+// Element offsets of the four taps (channel 0) in a 32-bit-strided image.
+__device__ __forceinline__ void tap_offsets(const Img32 &im, const Samp &s, int o[4])
 {
-    const long long base = (long long)b * im.sb + (long long)ch * im.sc;
-    const long long r0 = base + (long long)s.y0 * im.sh, r1 = r0 + im.sh;
-    const long long c0 = (long long)s.x0 * im.sw, c1 = c0 + im.sw;
-    v[0] = (s.inx0 && s.iny0) ? __ldg(im.p + r0 + c0) : 0.0f;
-    v[1] = (s.inx1 && s.iny0) ? __ldg(im.p + r0 + c1) : 0.0f;
-    v[2] = (s.inx0 && s.iny1) ? __ldg(im.p + r1 + c0) : 0.0f;
-    v[3] = (s.inx1 && s.iny1) ? __ldg(im.p + r1 + c1) : 0.0f;
+    o[0] = s.y0 * im.sh + s.x0 * im.sw;
+    o[1] = o[0] + im.sw;
+    o[2] = o[0] + im.sh;
+    o[3] = o[2] + im.sw;
+}
+
+template <bool IL>
+__device__ __forceinline__ void gather_taps(const Img32 &im, const Samp &s, const int o[4], int ch, float v[4])
+{
+    const int co = IL ? ch : ch * im.sc;
+    v[0] = s.in00 ? __ldg(im.p + o[0] + co) : 0.0f;
+    v[1] = s.in01 ? __ldg(im.p + o[1] + co) : 0.0f;
+    v[2] = s.in10 ? __ldg(im.p + o[2] + co) : 0.0f;
+    v[3] = s.in11 ? __ldg(im.p + o[3] + co) : 0.0f;
 }
 
 __device__ __forceinline__ float interp(const float v[4], const Samp &s)
@@ -147,15 +215,14 @@ __device__ __forceinline__ float interp(const float v[4], const Samp &s)
 // Shared-memory tile: NPL planes of RH x RP floats covering image rows [oy, oy+RH), cols [ox, ox+RP).
 // reflect_fixup() fills the one-pixel ring just outside the image (row -1 <- row 1, row H <- row H-2,
 // same for columns; corners via columns-then-rows), i.e. nn.ReflectionPad2d(1) (losses.py:18).
+// The caller has synchronised after filling; the caller synchronises again afterwards.
 // ------------------------------------------------------------------------------------------------
 template <int NPL, int RH, int RP>
 __device__ __forceinline__ void reflect_fixup(float *pl, int oy, int ox, int H, int W)
 {
     const bool touches = (oy < 0) || (ox < 0) || (oy + RH > H) || (ox + RP > W);
     if (!touches) return;   // uniform per CTA
-    __syncthreads();
-    // columns: image col -1 and col W, for in-image rows
-    for (int i = threadIdx.x; i < NPL * RH * 2; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NPL * RH * 2; i += blockDim.x) {      // columns -1 and W, in-image rows
         const int side = i & 1, r = (i >> 1) % RH, k = (i >> 1) / RH;
         const int y = oy + r;
         if (y < 0 || y >= H) continue;
@@ -165,7 +232,7 @@ __device__ __forceinline__ void reflect_fixup(float *pl, int oy, int ox, int H, 
         pl[(k * RH + r) * RP + lc] = pl[(k * RH + r) * RP + ls];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NPL * RP * 2; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NPL * RP * 2; i += blockDim.x) {      // rows -1 and H, all columns
         const int side = i & 1, c = (i >> 1) % RP, k = (i >> 1) / RP;
         const int x = ox + c;
         if (x < -1 || x > W) continue;
@@ -219,13 +286,15 @@ struct SsimVals {
     float mux, muy, A1, A2, B1, B2, n, dn, Q, sraw, s;
 };
 
-__device__ __forceinline__ void ssim_finish(const float S[5], const DivC d9, SsimVals &o)
+template <bool IEEE>
+__device__ __forceinline__ void ssim_finish(const float S[5], SsimVals &o)
 {
-    const float mux = xdivc(S[0], d9), muy = xdivc(S[1], d9);                  // losses.py:27-28
+    const float r9 = 1.0f / 9.0f;
+    const float mux = div_const<IEEE>(S[0], 9.0f, r9), muy = div_const<IEEE>(S[1], 9.0f, r9);      // losses.py:27-28
     const float mxx = xmul(mux, mux), myy = xmul(muy, muy), mxy = xmul(mux, muy);
-    const float vx = xsub(xdivc(S[2], d9), mxx);                                // :30-32
-    const float vy = xsub(xdivc(S[3], d9), myy);
-    const float vxy = xsub(xdivc(S[4], d9), mxy);
+    const float vx = xsub(div_const<IEEE>(S[2], 9.0f, r9), mxx);                                     // :30-32
+    const float vy = xsub(div_const<IEEE>(S[3], 9.0f, r9), myy);
+    const float vxy = xsub(div_const<IEEE>(S[4], 9.0f, r9), mxy);
     o.A1 = xadd(xmul(xmul(2.0f, mux), muy), C1F);                               // :34
     o.A2 = xadd(xmul(2.0f, vxy), C2F);
     o.B1 = xadd(xadd(mxx, myy), C1F);                                           // :35
@@ -241,60 +310,123 @@ __device__ __forceinline__ void ssim_finish(const float S[5], const DivC d9, Ssi
 
 // ------------------------------------------------------------------------------------------------
 // Phase 1: fill x / y planes for the region.  WARP: x = syn (*valid), y = tgt (*valid).
+// Returns true if this thread stored a value outside the fast-division range.
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int CK, int RH, int RP, int HALO, int TH, int TW>
-__device__ __forceinline__ void fill_region(const WPParams &p, const float *cam, int b, int ch0, int ty0, int tx0,
+template <int MODE, int CK, int RH, int RP, int HALO, int TH, int TW, bool IL>
+__device__ __forceinline__ bool fill_region(const WPParams &p, const float *cam, int b, int ch0, int ty0, int tx0,
                                             float *sx, float *sy, bool write_outputs)
 {
     const int oy = ty0 - HALO, ox = tx0 - HALO;
+    const int H = p.H, W = p.W;
+    const Img32 src = cta_image(p.src, b), tgt = cta_image(p.tgt, b);
+    const PixConst k = pix_const(p);
+    const bool use_mask = p.use_mask != 0;
+    const float *depth_b = p.depth + (long long)b * H * W;
+    bool bad = false;
     for (int i = threadIdx.x; i < RH * RP; i += blockDim.x) {
         const int hy = i / RP, hx = i - hy * RP;
         const int y = oy + hy, x = ox + hx;
-        if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        float *px = sx + hy * RP + hx, *py = sy + hy * RP + hx;
         if (MODE == MODE_WARP) {
-            const float d = __ldg(p.depth + ((long long)b * p.H + y) * p.W + x);
+            const int pixo = y * W + x;
+            const float d = __ldg(depth_b + pixo);
             Proj pr;
-            project_pixel(cam, p, x, y, d, pr);
+            project_pixel(cam, k, x, y, d, pr);
             Samp s;
-            sampler_setup(p, pr.gx, pr.gy, s);
+            sampler_setup(k, pr.gx, pr.gy, s);
+            int o[4];
+            tap_offsets(src, s, o);
+            const float *tp = tgt.p + y * tgt.sh + x * tgt.sw;
             const bool centre = write_outputs && hy >= HALO && hy < HALO + TH && hx >= HALO && hx < HALO + TW;
-            const long long pixi = ((long long)b * p.H + y) * p.W + x;
             if (centre) {
+                const long long pixi = (long long)b * H * W + pixo;
                 if (p.valid) p.valid[pixi] = pr.valid;
                 if (p.pix) { p.pix[pixi * 2] = pr.gx; p.pix[pixi * 2 + 1] = pr.gy; }
             }
-            const long long tbase = (long long)b * p.tgt.sb + (long long)y * p.tgt.sh + (long long)x * p.tgt.sw;
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
                 float v[4];
-                gather_taps(p.src, b, s, ch, v);
-                const float o = interp(v, s);
-                const float t = __ldg(p.tgt.p + tbase + ch * p.tgt.sc);
-                sx[(ch * RH + hy) * RP + hx] = p.use_mask ? xmul(o, pr.valid) : o;    // train_depth.py:714-715
-                sy[(ch * RH + hy) * RP + hx] = p.use_mask ? xmul(t, pr.valid) : t;
-                if (centre && p.syn) p.syn[(((long long)b * 3 + ch) * p.H + y) * p.W + x] = o;
+                gather_taps<IL>(src, s, o, ch, v);
+                const float sv = interp(v, s);
+                const float t = __ldg(tp + (IL ? ch : ch * tgt.sc));
+                const float xv = use_mask ? xmul(sv, pr.valid) : sv;        // train_depth.py:714-715
+                const float yv = use_mask ? xmul(t, pr.valid) : t;
+                px[ch * RH * RP] = xv;
+                py[ch * RH * RP] = yv;
+                bad |= value_out_of_fast_range(xv) | value_out_of_fast_range(yv);
+                if (centre && p.syn) p.syn[((long long)b * 3 + ch) * H * W + pixo] = sv;
             }
         } else {
-            const long long xb = (long long)b * p.src.sb + (long long)y * p.src.sh + (long long)x * p.src.sw;
-            const long long yb = (long long)b * p.tgt.sb + (long long)y * p.tgt.sh + (long long)x * p.tgt.sw;
+            const float *xp = src.p + y * src.sh + x * src.sw, *yp = tgt.p + y * tgt.sh + x * tgt.sw;
 #pragma unroll
             for (int ch = 0; ch < CK; ch++) {
-                sx[(ch * RH + hy) * RP + hx] = __ldg(p.src.p + xb + (long long)(ch0 + ch) * p.src.sc);
-                sy[(ch * RH + hy) * RP + hx] = __ldg(p.tgt.p + yb + (long long)(ch0 + ch) * p.tgt.sc);
+                const float xv = __ldg(xp + (long long)(ch0 + ch) * src.sc), yv = __ldg(yp + (long long)(ch0 + ch) * tgt.sc);
+                px[ch * RH * RP] = xv;
+                py[ch * RH * RP] = yv;
+                bad |= value_out_of_fast_range(xv) | value_out_of_fast_range(yv);
             }
         }
     }
+    return bad;
 }
 
 // ================================================================================================
 // Forward kernel
 // ================================================================================================
-template <int MODE, int CK, int TH, int TW, int NT>
+template <bool IEEE, int CK, int TH, int TW, int NT>
+__device__ __forceinline__ void fwd_phase2(const WPParams &p, const float *sx, const float *sy, float *red,
+                                           int b, int ch0, int ty0, int tx0)
+{
+    constexpr int RH = TH + 2, RP = TW + 2, NP = TH * TW / NT;
+    const int H = p.H, W = p.W;
+    const int col = threadIdx.x % TW, rg = threadIdx.x / TW;
+    const int x = tx0 + col;
+    float ssum[NP], lsum[NP];
+#pragma unroll
+    for (int ch = 0; ch < CK; ch++) {
+        float S[NP][5];
+        const float *wx = sx + (ch * RH + rg * NP) * RP + col;
+        const float *wy = sy + (ch * RH + rg * NP) * RP + col;
+        window_sums<NP, RP>(wx, wy, S);
+#pragma unroll
+        for (int pp = 0; pp < NP; pp++) {
+            SsimVals v;
+            ssim_finish<IEEE>(S[pp], v);
+            const float cx = wx[(pp + 1) * RP + 1], cy = wy[(pp + 1) * RP + 1];
+            const float l1 = fabsf(xsub(cy, cx));                                // losses.py:112
+            const int y = ty0 + rg * NP + pp;
+            if (p.ssim && y < H && x < W)
+                p.ssim[(((long long)b * p.C + ch0 + ch) * H + y) * W + x] = v.s;
+            if (ch == 0) { ssum[pp] = v.s; lsum[pp] = l1; }
+            else { ssum[pp] = xadd(ssum[pp], v.s); lsum[pp] = xadd(lsum[pp], l1); }
+        }
+    }
+    if (CK == 3 && (p.loss_map || p.partial)) {
+        float acc = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NP; pp++) {
+            const int y = ty0 + rg * NP + pp;
+            if (y < H && x < W) {
+                const float r3 = 1.0f / 3.0f;
+                const float sm = div_const<IEEE>(ssum[pp], 3.0f, r3), lm = div_const<IEEE>(lsum[pp], 3.0f, r3);   // .mean(1, True)
+                const float l = xadd(xmul(0.85f, sm), xmul(0.15f, lm));               // losses.py:115
+                if (p.loss_map) p.loss_map[((long long)b * H + y) * W + x] = l;
+                acc += l;
+            }
+        }
+        if (p.partial) {
+            const float tot = block_sum(acc, red);
+            if (threadIdx.x == 0) p.partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+        }
+    }
+}
+
+template <int MODE, int CK, int TH, int TW, int NT, bool IL>
 __global__ void __launch_bounds__(NT) warp_photo_fwd_kernel(const __grid_constant__ WPParams p)
 {
     constexpr int RH = TH + 2, RP = TW + 2;
-    constexpr int NP = TH * TW / NT;               // centres per thread (vertical strip)
-    static_assert(TH * TW % NT == 0 && NT % TW == 0 && (NT / TW) * NP == TH, "tile / thread mapping");
+    static_assert(TH * TW % NT == 0 && NT % TW == 0 && (NT / TW) * (TH * TW / NT) == TH, "tile / thread mapping");
     __shared__ float sx[CK * RH * RP];
     __shared__ float sy[CK * RH * RP];
     __shared__ float cam[24];
@@ -308,50 +440,13 @@ __global__ void __launch_bounds__(NT) warp_photo_fwd_kernel(const __grid_constan
         stage_camera(p, b, cam);
         __syncthreads();
     }
-    fill_region<MODE, CK, RH, RP, 1, TH, TW>(p, cam, b, ch0, ty0, tx0, sx, sy, true);
+    const bool bad = fill_region<MODE, CK, RH, RP, 1, TH, TW, IL>(p, cam, b, ch0, ty0, tx0, sx, sy, true);
+    const int slow = __syncthreads_or(bad ? 1 : 0) | !p.div_exact;
     reflect_fixup<CK, RH, RP>(sx, ty0 - 1, tx0 - 1, p.H, p.W);
     reflect_fixup<CK, RH, RP>(sy, ty0 - 1, tx0 - 1, p.H, p.W);
     __syncthreads();
-
-    const int col = threadIdx.x % TW, rg = threadIdx.x / TW;
-    const int x = tx0 + col;
-    float ssum[NP], lsum[NP];
-#pragma unroll
-    for (int ch = 0; ch < CK; ch++) {
-        float S[NP][5];
-        const float *wx = sx + (ch * RH + rg * NP) * RP + col;
-        const float *wy = sy + (ch * RH + rg * NP) * RP + col;
-        window_sums<NP, RP>(wx, wy, S);
-#pragma unroll
-        for (int pp = 0; pp < NP; pp++) {
-            SsimVals v;
-            ssim_finish(S[pp], p.d9, v);
-            const float cx = wx[(pp + 1) * RP + 1], cy = wy[(pp + 1) * RP + 1];
-            const float l1 = fabsf(xsub(cy, cx));                                // losses.py:112
-            const int y = ty0 + rg * NP + pp;
-            if (p.ssim && y < p.H && x < p.W)
-                p.ssim[(((long long)b * p.C + ch0 + ch) * p.H + y) * p.W + x] = v.s;
-            if (ch == 0) { ssum[pp] = v.s; lsum[pp] = l1; }
-            else { ssum[pp] = xadd(ssum[pp], v.s); lsum[pp] = xadd(lsum[pp], l1); }
-        }
-    }
-    if (CK == 3 && (p.loss_map || p.partial)) {
-        float acc = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < NP; pp++) {
-            const int y = ty0 + rg * NP + pp;
-            if (y < p.H && x < p.W) {
-                const float sm = xdivc(ssum[pp], p.d3), lm = xdivc(lsum[pp], p.d3);   // .mean(1, True)
-                const float l = xadd(xmul(0.85f, sm), xmul(0.15f, lm));               // losses.py:115
-                if (p.loss_map) p.loss_map[((long long)b * p.H + y) * p.W + x] = l;
-                acc += l;
-            }
-        }
-        if (p.partial) {
-            const float tot = block_sum(acc, red);
-            if (threadIdx.x == 0) p.partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
-        }
-    }
+    if (slow) fwd_phase2<true, CK, TH, TW, NT>(p, sx, sy, red, b, ch0, ty0, tx0);
+    else fwd_phase2<false, CK, TH, TW, NT>(p, sx, sy, red, b, ch0, ty0, tx0);
 }
 
 // Deterministic final reduction of per-CTA partial sums: out[0] = sum(partial[0..n)) * scale.
@@ -390,45 +485,14 @@ __global__ void __launch_bounds__(256) reduce_gP_kernel(const float *partial, in
 // ================================================================================================
 // Backward kernel
 // ================================================================================================
-__device__ __forceinline__ float upstream_loss_grad(const WPParams &p, int b, int y, int x)
+template <bool IEEE, int CK, int TH, int TW, int NT, bool NEED_GY>
+__device__ __forceinline__ void bwd_phaseB(const WPParams &p, const float *sx, const float *sy, float *G,
+                                           int b, int ch0, int ty0, int tx0, float gscal)
 {
-    if (p.g_loss_map) return __ldg(p.g_loss_map + ((long long)b * p.H + y) * p.W + x);
-    if (p.g_ssim) return 0.0f;                       // stand-alone SSIM backward with only grad_ssim
-    return (p.g_scalar ? __ldg(p.g_scalar) : 1.0f) * p.g_scale;
-}
-
-template <int MODE, int CK, int TH, int TW, int NT, bool NEED_GY>
-__global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constant__ WPParams p)
-{
-    constexpr int RH2 = TH + 4, RP2 = TW + 4;      // x / y region (2-pixel halo)
-    constexpr int RH1 = TH + 2, RP1 = TW + 2;      // centre region (1-pixel halo)
-    constexpr int NG = NEED_GY ? 4 : 3;            // coefficient planes per channel
-    constexpr int NPB = RH1 / 3;                   // centres per strip in phase B
-    constexpr int NPC = TH * TW / NT;              // owners per thread in phase C
-    static_assert(RH1 % 3 == 0 && TH * TW % NT == 0 && NT % TW == 0 && (NT / TW) * NPC == TH, "tile / thread mapping");
-    extern __shared__ float smem[];
-    float *sx = smem;                              // [CK][RH2][RP2]
-    float *sy = sx + CK * RH2 * RP2;
-    float *G = sy + CK * RH2 * RP2;                // [CK][NG][RH1][RP1]
-    float *cam = G + CK * NG * RH1 * RP1;          // 24
-    float *red = cam + 24;                         // NT/32 * 12
-
-    const int planes_per_b = (MODE == MODE_DIRECT) ? p.C / CK : 1;
-    const int b = blockIdx.z / planes_per_b, ch0 = (blockIdx.z % planes_per_b) * CK;
-    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    constexpr int RH2 = TH + 4, RP2 = TW + 4, RH1 = TH + 2, RP1 = TW + 2;
+    constexpr int NG = NEED_GY ? 4 : 3, NPB = RH1 / 3;
+    const int H = p.H, W = p.W;
     const float invC = 1.0f / (float)p.C;
-
-    if (MODE == MODE_WARP) {
-        stage_camera(p, b, cam);
-        __syncthreads();
-    }
-    // ---- phase A ---------------------------------------------------------------------------
-    fill_region<MODE, CK, RH2, RP2, 2, TH, TW>(p, cam, b, ch0, ty0, tx0, sx, sy, false);
-    reflect_fixup<CK, RH2, RP2>(sx, ty0 - 2, tx0 - 2, p.H, p.W);
-    reflect_fixup<CK, RH2, RP2>(sy, ty0 - 2, tx0 - 2, p.H, p.W);
-    __syncthreads();
-
-    // ---- phase B: coefficient planes at every centre of the 1-pixel halo ----------------------
     for (int task = threadIdx.x; task < 3 * RP1; task += NT) {
         const int cg = task / RP1, cc = task - cg * RP1;      // strip cg covers centre rows cg*NPB .. +NPB-1
         const int cx = tx0 - 1 + cc;
@@ -442,19 +506,22 @@ __global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constan
             for (int pp = 0; pp < NPB; pp++) {
                 const int cr = cg * NPB + pp, cy = ty0 - 1 + cr;
                 float ga = 0.f, gb = 0.f, gc = 0.f, gay = 0.f;
-                if (cy >= 0 && cy < p.H && cx >= 0 && cx < p.W) {
+                if (cy >= 0 && cy < H && cx >= 0 && cx < W) {
                     SsimVals v;
-                    ssim_finish(S[pp], p.d9, v);
-                    float gs = 0.85f * invC * upstream_loss_grad(p, b, cy, cx);
-                    if (p.g_ssim) gs += __ldg(p.g_ssim + (((long long)b * p.C + ch0 + ch) * p.H + cy) * p.W + cx);
+                    ssim_finish<IEEE>(S[pp], v);
+                    float gl = gscal;
+                    if (p.g_loss_map) gl = __ldg(p.g_loss_map + ((long long)b * H + cy) * W + cx);
+                    float gs = 0.85f * invC * gl;
+                    if (p.g_ssim) gs += __ldg(p.g_ssim + (((long long)b * p.C + ch0 + ch) * H + cy) * W + cx);
                     if (!(v.sraw >= 0.0f && v.sraw <= 1.0f)) gs = 0.0f;       // clamp passes gradient on [0,1]
-                    const float rdn = 1.0f / v.dn;
+                    const float rdn = __frcp_rn(v.dn);
                     const float dA = v.A2 - v.A1, dB = v.B2 - v.B1;
-                    const float h = (-0.5f / 9.0f) * gs;                       // d ssim/dQ = -1/2, box filter 1/9
-                    ga = h * (2.0f * v.muy * dA - v.Q * 2.0f * v.mux * dB) * rdn;
-                    gb = h * (-v.Q * v.B1) * rdn;
-                    gc = h * (2.0f * v.A1) * rdn;
-                    if (NEED_GY) gay = h * (2.0f * v.mux * dA - v.Q * 2.0f * v.muy * dB) * rdn;
+                    const float h = (-0.5f / 9.0f) * gs * rdn;                 // d ssim/dQ = -1/2, box filter 1/9
+                    const float tq = 2.0f * v.Q;
+                    ga = h * (2.0f * v.muy * dA - tq * v.mux * dB);
+                    gb = -h * v.Q * v.B1;
+                    gc = h * 2.0f * v.A1;
+                    if (NEED_GY) gay = h * (2.0f * v.mux * dA - tq * v.muy * dB);
                 }
                 float *g = G + ((ch * NG) * RH1 + cr) * RP1 + cc;
                 g[0] = ga;
@@ -464,6 +531,46 @@ __global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constan
             }
         }
     }
+}
+
+template <int MODE, int CK, int TH, int TW, int NT, bool NEED_GY, bool IL>
+__global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constant__ WPParams p)
+{
+    constexpr int RH2 = TH + 4, RP2 = TW + 4;      // x / y region (2-pixel halo)
+    constexpr int RH1 = TH + 2, RP1 = TW + 2;      // centre region (1-pixel halo)
+    constexpr int NG = NEED_GY ? 4 : 3;            // coefficient planes per channel
+    constexpr int NPC = TH * TW / NT;              // owners per thread in phase C
+    static_assert(RH1 % 3 == 0 && TH * TW % NT == 0 && NT % TW == 0 && (NT / TW) * NPC == TH, "tile / thread mapping");
+    extern __shared__ float smem[];
+    float *sx = smem;                              // [CK][RH2][RP2]
+    float *sy = sx + CK * RH2 * RP2;
+    float *G = sy + CK * RH2 * RP2;                // [CK][NG][RH1][RP1]
+    float *cam = G + CK * NG * RH1 * RP1;          // 24
+    float *red = cam + 24;                         // NT/32 * 12
+
+    const int planes_per_b = (MODE == MODE_DIRECT) ? p.C / CK : 1;
+    const int b = blockIdx.z / planes_per_b, ch0 = (blockIdx.z % planes_per_b) * CK;
+    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const int H = p.H, W = p.W;
+    const float invC = 1.0f / (float)p.C;
+    // uniform upstream gradient when no per-pixel map is given
+    float gscal = 0.0f;
+    if (!p.g_loss_map && !p.g_ssim) gscal = (p.g_scalar ? __ldg(p.g_scalar) : 1.0f) * p.g_scale;
+
+    if (MODE == MODE_WARP) {
+        stage_camera(p, b, cam);
+        __syncthreads();
+    }
+    // ---- phase A ---------------------------------------------------------------------------
+    const bool bad = fill_region<MODE, CK, RH2, RP2, 2, TH, TW, IL>(p, cam, b, ch0, ty0, tx0, sx, sy, false);
+    const int slow = __syncthreads_or(bad ? 1 : 0) | !p.div_exact;
+    reflect_fixup<CK, RH2, RP2>(sx, ty0 - 2, tx0 - 2, H, W);
+    reflect_fixup<CK, RH2, RP2>(sy, ty0 - 2, tx0 - 2, H, W);
+    __syncthreads();
+
+    // ---- phase B: coefficient planes at every centre of the 1-pixel halo ----------------------
+    if (slow) bwd_phaseB<true, CK, TH, TW, NT, NEED_GY>(p, sx, sy, G, b, ch0, ty0, tx0, gscal);
+    else bwd_phaseB<false, CK, TH, TW, NT, NEED_GY>(p, sx, sy, G, b, ch0, ty0, tx0, gscal);
     __syncthreads();
 
     // ---- phase C: owners ---------------------------------------------------------------------
@@ -474,27 +581,33 @@ __global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constan
 #pragma unroll
     for (int dx = -1; dx <= 1; dx++) {
         const int cx = x + dx;
-        float w = (cx >= 0 && cx < p.W) ? 1.0f : 0.0f;
-        if (dx != 0 && ((cx == 0 && x == 1) || (cx == p.W - 1 && x == p.W - 2))) w += 1.0f;
+        float w = (cx >= 0 && cx < W) ? 1.0f : 0.0f;
+        if (dx != 0 && ((cx == 0 && x == 1) || (cx == W - 1 && x == W - 2))) w += 1.0f;
         wcol[dx + 1] = w;
     }
     float gP[12];
 #pragma unroll
     for (int e = 0; e < 12; e++) gP[e] = 0.f;
+    const Img32 src = cta_image(p.src, b);
+    const PixConst kc = pix_const(p);
+    const bool use_mask = p.use_mask != 0;
+    float *gsrc_b = p.g_src.p ? p.g_src.p + (long long)b * p.g_src.sb : nullptr;
+    const int gs_sc = (int)p.g_src.sc, gs_sh = (int)p.g_src.sh, gs_sw = (int)p.g_src.sw;
 
 #pragma unroll
     for (int pp = 0; pp < NPC; pp++) {
         const int row = rg * NPC + pp, y = ty0 + row;
-        const bool inside = (y < p.H && x < p.W);
+        const bool inside = (y < H && x < W);
         float wrow[3];
 #pragma unroll
         for (int dy = -1; dy <= 1; dy++) {
             const int cy = y + dy;
-            float w = (cy >= 0 && cy < p.H) ? 1.0f : 0.0f;
-            if (dy != 0 && ((cy == 0 && y == 1) || (cy == p.H - 1 && y == p.H - 2))) w += 1.0f;
+            float w = (cy >= 0 && cy < H) ? 1.0f : 0.0f;
+            if (dy != 0 && ((cy == 0 && y == 1) || (cy == H - 1 && y == H - 2))) w += 1.0f;
             wrow[dy + 1] = w;
         }
-        const float gl = inside ? upstream_loss_grad(p, b, y, x) : 0.0f;
+        float gl = gscal;
+        if (p.g_loss_map && inside) gl = __ldg(p.g_loss_map + ((long long)b * H + y) * W + x);
         const float gl1 = 0.15f * invC * gl;
         float gsyn[CK];
 #pragma unroll
@@ -517,42 +630,44 @@ __global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constan
             const float gxj = acc[0] + 2.0f * xj * acc[1] + yj * acc[2] + gl1 * sg;
             gsyn[ch] = gxj;
             if (MODE == MODE_DIRECT && inside) {
-                const long long o = (((long long)b * p.C + ch0 + ch) * p.H + y) * p.W + x;
+                const long long o = (((long long)b * p.C + ch0 + ch) * H + y) * W + x;
                 if (p.g_x) p.g_x[o] = gxj;
                 if (NEED_GY && p.g_y) p.g_y[o] = acc[NG - 1] + 2.0f * yj * acc[1] + xj * acc[2] - gl1 * sg;
             }
         }
         if (MODE == MODE_WARP && inside) {
-            const long long pixi = ((long long)b * p.H + y) * p.W + x;
+            const int pixo = y * W + x;
+            const long long pixi = (long long)b * H * W + pixo;
             const float d = __ldg(p.depth + pixi);
             Proj pr;
-            project_pixel(cam, p, x, y, d, pr);
+            project_pixel(cam, kc, x, y, d, pr);
             Samp s;
-            sampler_setup(p, pr.gx, pr.gy, s);
+            sampler_setup(kc, pr.gx, pr.gy, s);
+            int o[4];
+            tap_offsets(src, s, o);
+            const int go0 = s.y0 * gs_sh + s.x0 * gs_sw;
             float gix = 0.f, giy = 0.f;
-            const float ex = 1.0f - (s.ix - floorf(s.ix)), wxx = s.ix - floorf(s.ix);
-            const float ey = 1.0f - (s.iy - floorf(s.iy)), wyy = s.iy - floorf(s.iy);
+            const float wxx = s.ix - floorf(s.ix), ex = 1.0f - wxx;
+            const float wyy = s.iy - floorf(s.iy), ey = 1.0f - wyy;
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-                const float gsy = p.use_mask ? gsyn[ch] * pr.valid : gsyn[ch];
+                const float gsy = use_mask ? gsyn[ch] * pr.valid : gsyn[ch];
                 float v[4];
-                gather_taps(p.src, b, s, ch, v);
+                gather_taps<IL>(src, s, o, ch, v);
                 gix += gsy * ((v[1] - v[0]) * ey + (v[3] - v[2]) * wyy);
                 giy += gsy * ((v[2] - v[0]) * ex + (v[3] - v[1]) * wxx);
-                if (p.g_src.p) {
-                    const long long base = (long long)b * p.g_src.sb + (long long)ch * p.g_src.sc;
-                    const long long r0 = base + (long long)s.y0 * p.g_src.sh, r1 = r0 + p.g_src.sh;
-                    const long long c0 = (long long)s.x0 * p.g_src.sw, c1 = c0 + p.g_src.sw;
-                    if (s.inx0 && s.iny0) atomicAdd(p.g_src.p + r0 + c0, gsy * s.nw);
-                    if (s.inx1 && s.iny0) atomicAdd(p.g_src.p + r0 + c1, gsy * s.ne);
-                    if (s.inx0 && s.iny1) atomicAdd(p.g_src.p + r1 + c0, gsy * s.sw);
-                    if (s.inx1 && s.iny1) atomicAdd(p.g_src.p + r1 + c1, gsy * s.se);
+                if (gsrc_b) {
+                    float *gp = gsrc_b + go0 + ch * gs_sc;
+                    if (s.in00) atomicAdd(gp, gsy * s.nw);
+                    if (s.in01) atomicAdd(gp + gs_sw, gsy * s.ne);
+                    if (s.in10) atomicAdd(gp + gs_sh, gsy * s.sw);
+                    if (s.in11) atomicAdd(gp + gs_sh + gs_sw, gsy * s.se);
                 }
             }
             // sample position -> pixel coordinate -> camera point        
-            const float gu = gix * s.mx * (p.half_w * 2.0f / p.wm1);
-            const float gv = giy * s.my * (p.half_h * 2.0f / p.hm1);
-            const float rz = 1.0f / pr.z;
+            const float gu = gix * s.mx * (kc.half_w * 2.0f / kc.wm1);
+            const float gv = giy * s.my * (kc.half_h * 2.0f / kc.hm1);
+            const float rz = __frcp_rn(pr.z);
             const float gc0 = gu * rz, gc1 = gv * rz;
             const float gc2 = -(gu * pr.c0 + gv * pr.c1) * rz * rz;
             const float *P = cam + 9;
@@ -561,7 +676,7 @@ __global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constan
             const float q2 = P[8] * pr.r0 + P[9] * pr.r1 + P[10] * pr.r2;
             // d u/d depth = (q0*tz - t0*q2)/z^2 with c = depth*q + t: the well-conditioned form of
             // gc . q (which cancels ~100x in fp32); agrees with exact arithmetic to ~4e-7.
-            const float tz = P[11] + p.eps;
+            const float tz = P[11] + kc.eps;
             const float du = q0 * tz - P[3] * q2, dv = q1 * tz - P[7] * q2;
             p.g_depth[pixi] = (gu * du + gv * dv) * rz * rz;
             gP[0] += gc0 * pr.X0; gP[1] += gc0 * pr.X1; gP[2] += gc0 * pr.X2; gP[3] += gc0;
@@ -604,17 +719,17 @@ static size_t partial_count(int B, int H, int W)
     return (size_t)g.x * g.y * g.z;
 }
 
-template <int MODE, int CK, bool NEED_GY>
+template <int CK, bool NEED_GY>
 static constexpr size_t bwd_smem_bytes()
 {
     return sizeof(float) * (2 * CK * (B_TH + 4) * (B_TW + 4) + CK * (NEED_GY ? 4 : 3) * (B_TH + 2) * (B_TW + 2) + 24 + (B_NT / 32) * 12);
 }
 
-template <int MODE, int CK, bool NEED_GY>
+template <int MODE, int CK, bool NEED_GY, bool IL>
 static int launch_bwd(const WPParams &p, dim3 grid, cudaStream_t st)
 {
-    auto kern = warp_photo_bwd_kernel<MODE, CK, B_TH, B_TW, B_NT, NEED_GY>;
-    constexpr size_t smem = bwd_smem_bytes<MODE, CK, NEED_GY>();
+    auto kern = warp_photo_bwd_kernel<MODE, CK, B_TH, B_TW, B_NT, NEED_GY, IL>;
+    constexpr size_t smem = bwd_smem_bytes<CK, NEED_GY>();
     static bool configured = false;
     if (!configured) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -626,17 +741,34 @@ static int launch_bwd(const WPParams &p, dim3 grid, cudaStream_t st)
     return finish_launch("warp_photo_bwd_kernel");
 }
 
+static bool view_fits_int32(const ImgView &v, int C, int H, int W)
+{
+    const long long ext = llabs(v.sc) * (C - 1) + llabs(v.sh) * (H - 1) + llabs(v.sw) * (W - 1);
+    return ext < (1ll << 30) && llabs(v.sc) < (1ll << 30) && llabs(v.sh) < (1ll << 30) && llabs(v.sw) < (1ll << 30);
+}
+
 static int fill_common(WPParams &p, int B, int C, int H, int W, int padding_mode, int use_mask, float eps, cudaStream_t st)
 {
     E2E_REQUIRE(B > 0 && H >= 2 && W >= 2, "B=%d H=%d W=%d: need B>0, H>=2, W>=2 (reflection padding)", B, H, W);
     E2E_REQUIRE(padding_mode == 0 || padding_mode == 1, "padding_mode must be 0 (zeros) or 1 (border)");
     E2E_REQUIRE((long long)B * C <= 65535, "B*C exceeds gridDim.z");
+    E2E_REQUIRE((long long)H * W * 3 < (1ll << 30), "image too large for 32-bit in-image offsets");
     p.B = B; p.C = C; p.H = H; p.W = W;
     p.border = padding_mode; p.use_mask = use_mask; p.eps = eps;
     p.wm1 = (float)(W - 1); p.hm1 = (float)(H - 1);
     p.half_w = (float)W / 2; p.half_h = (float)H / 2;
-    p.dW = host_divc(p.wm1, st); p.dH = host_divc(p.hm1, st);
-    p.d9 = host_divc(9.0f, st); p.d3 = host_divc(3.0f, st);
+    const DivC dW = host_divc(p.wm1, st), dH = host_divc(p.hm1, st), d9 = host_divc(9.0f, st), d3 = host_divc(3.0f, st);
+    p.rcpW = dW.rcp; p.rcpH = dH.rcp;
+    p.div_exact = dW.exact && dH.exact && d9.exact && d3.exact;
+    return 0;
+}
+
+static int set_views(WPParams &p, const float *a, const int64_t as[4], const float *b, const int64_t bs[4], int C)
+{
+    p.src = make_view(a, as);
+    p.tgt = make_view(b, bs);
+    E2E_REQUIRE(view_fits_int32(p.src, C, p.H, p.W) && view_fits_int32(p.tgt, C, p.H, p.W),
+                "image strides do not fit 32-bit in-image offsets");
     return 0;
 }
 
@@ -663,7 +795,7 @@ int e2e_warp_photo_fwd(const float *depth, const float *inv_K, const float *K, c
     E2E_REQUIRE(depth && inv_K && K && T && src && tgt, "null input pointer");
     if (int rc = fill_common(p, B, 3, H, W, padding_mode, use_mask, eps, st)) return rc;
     p.depth = depth; p.inv_K = inv_K; p.K = K; p.T = T;
-    p.src = make_view(src, src_strides); p.tgt = make_view(tgt, tgt_strides);
+    if (int rc = set_views(p, src, src_strides, tgt, tgt_strides, 3)) return rc;
     p.syn = syn; p.valid = valid; p.pix = pix; p.loss_map = loss_map;
     const dim3 grid = tile_grid(B, H, W, F_TH, F_TW);
     const size_t nct = (size_t)grid.x * grid.y * grid.z;
@@ -671,7 +803,9 @@ int e2e_warp_photo_fwd(const float *depth, const float *inv_K, const float *K, c
         E2E_REQUIRE(workspace && workspace_bytes >= nct * sizeof(float), "workspace too small for loss_mean");
         p.partial = (float *)workspace;
     }
-    warp_photo_fwd_kernel<MODE_WARP, 3, F_TH, F_TW, F_NT><<<grid, F_NT, 0, st>>>(p);
+    const bool il = (p.src.sc == 1 && p.tgt.sc == 1);     // interleaved RGB (channels-last memory)
+    if (il) warp_photo_fwd_kernel<MODE_WARP, 3, F_TH, F_TW, F_NT, true><<<grid, F_NT, 0, st>>>(p);
+    else warp_photo_fwd_kernel<MODE_WARP, 3, F_TH, F_TW, F_NT, false><<<grid, F_NT, 0, st>>>(p);
     count_launch();
     if (int rc = finish_launch("warp_photo_fwd_kernel")) return rc;
     if (loss_mean) {
@@ -694,12 +828,14 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
     E2E_REQUIRE(depth && inv_K && K && T && src && tgt && grad_depth, "null pointer");
     if (int rc = fill_common(p, B, 3, H, W, padding_mode, use_mask, eps, st)) return rc;
     p.depth = depth; p.inv_K = inv_K; p.K = K; p.T = T;
-    p.src = make_view(src, src_strides); p.tgt = make_view(tgt, tgt_strides);
+    if (int rc = set_views(p, src, src_strides, tgt, tgt_strides, 3)) return rc;
     p.g_loss_map = grad_loss_map; p.g_scalar = grad_scalar; p.g_scale = scalar_scale;
     p.g_depth = grad_depth;
     if (grad_src) {
         E2E_REQUIRE(grad_src_strides, "grad_src needs strides");
         p.g_src = make_view_w(grad_src, grad_src_strides);
+        const ImgView gv{grad_src, p.g_src.sb, p.g_src.sc, p.g_src.sh, p.g_src.sw};
+        E2E_REQUIRE(view_fits_int32(gv, 3, H, W), "grad_src strides do not fit 32-bit in-image offsets");
     }
     const dim3 grid = tile_grid(B, H, W, B_TH, B_TW);
     const size_t nct = (size_t)grid.x * grid.y * grid.z;
@@ -707,7 +843,8 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
         E2E_REQUIRE(workspace && workspace_bytes >= nct * 12 * sizeof(float), "workspace too small for grad_P");
         p.gP_partial = (float *)workspace;
     }
-    if (int rc = launch_bwd<MODE_WARP, 3, false>(p, grid, st)) return rc;
+    const bool il = (p.src.sc == 1 && p.tgt.sc == 1);
+    if (int rc = il ? launch_bwd<MODE_WARP, 3, false, true>(p, grid, st) : launch_bwd<MODE_WARP, 3, false, false>(p, grid, st)) return rc;
     if (grad_P) {
         reduce_gP_kernel<<<B * 12, 256, 0, st>>>(p.gP_partial, (int)(grid.x * grid.y), grad_P);
         count_launch();
@@ -724,14 +861,14 @@ int e2e_ssim_fwd(const float *x, const int64_t x_strides[4], const float *y, con
     E2E_REQUIRE(x && y && C >= 1, "null input / bad C");
     E2E_REQUIRE(!loss_map || C == 3, "loss_map output requires C == 3 (photometric_loss, losses.py:97-117)");
     if (int rc = fill_common(p, B, C, H, W, 1, 0, 0.f, st)) return rc;
-    p.src = make_view(x, x_strides); p.tgt = make_view(y, y_strides);
+    if (int rc = set_views(p, x, x_strides, y, y_strides, C)) return rc;
     p.ssim = ssim_map; p.loss_map = loss_map;
     dim3 grid = tile_grid(B, H, W, F_TH, F_TW);
     if (C == 3) {
-        warp_photo_fwd_kernel<MODE_DIRECT, 3, F_TH, F_TW, F_NT><<<grid, F_NT, 0, st>>>(p);
+        warp_photo_fwd_kernel<MODE_DIRECT, 3, F_TH, F_TW, F_NT, false><<<grid, F_NT, 0, st>>>(p);
     } else {
         grid.z = B * C;
-        warp_photo_fwd_kernel<MODE_DIRECT, 1, F_TH, F_TW, F_NT><<<grid, F_NT, 0, st>>>(p);
+        warp_photo_fwd_kernel<MODE_DIRECT, 1, F_TH, F_TW, F_NT, false><<<grid, F_NT, 0, st>>>(p);
     }
     count_launch();
     return finish_launch("ssim_fwd_kernel");
@@ -746,13 +883,13 @@ int e2e_ssim_bwd(const float *x, const int64_t x_strides[4], const float *y, con
     E2E_REQUIRE(x && y && C >= 1 && (grad_ssim || grad_loss_map), "null input / no upstream gradient");
     E2E_REQUIRE(!grad_loss_map || C == 3, "grad_loss_map requires C == 3");
     if (int rc = fill_common(p, B, C, H, W, 1, 0, 0.f, st)) return rc;
-    p.src = make_view(x, x_strides); p.tgt = make_view(y, y_strides);
+    if (int rc = set_views(p, x, x_strides, y, y_strides, C)) return rc;
     p.g_ssim = grad_ssim; p.g_loss_map = grad_loss_map;
     p.g_x = grad_x; p.g_y = grad_y;
     dim3 grid = tile_grid(B, H, W, B_TH, B_TW);
-    if (C == 3) return launch_bwd<MODE_DIRECT, 3, true>(p, grid, st);
+    if (C == 3) return launch_bwd<MODE_DIRECT, 3, true, false>(p, grid, st);
     grid.z = B * C;
-    return launch_bwd<MODE_DIRECT, 1, true>(p, grid, st);
+    return launch_bwd<MODE_DIRECT, 1, true, false>(p, grid, st);
 }
 
 }  // extern "C"

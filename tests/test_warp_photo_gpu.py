@@ -159,18 +159,24 @@ def test_batch_independence_full_size(e2e):
         assert torch.equal(one, full[b:b + 1])
 
 
-def test_identity_warp_gives_zero_loss(e2e):
-    """Known answer: T = I and source == target => synthesized == target on every valid pixel, so
-    SSIM loss and L1 are exactly 0 in the interior."""
+def test_identity_pose_known_answer(e2e):
+    """Known answer for T = I: the projected pixel is the pixel itself, so the reference's grid is
+    gx = (x/(W-1) - 0.5)*2 -- and because that grid is then read with align_corners=False the sample
+    position is x*W/(W-1) - 0.5, NOT x (SURVEY.md section 7 "parity quirks").  Both are checked."""
     from e2e_slam_b200.synthetic import make_pairs
-    d = make_pairs(1, 48, 64, "tum", seed=2)
+    H, W = 48, 64
+    d = make_pairs(1, H, W, "tum", seed=2)
     dev = {k: v.cuda() for k, v in d.items()}
     img = dev["colors"][:, 1].permute(0, 3, 1, 2)
     T = torch.eye(4, device="cuda").unsqueeze(0)
     lm, syn, valid, pix = e2e.warp_photometric(dev["depth"], dev["inv_K"], dev["K"], T, img, img, need_outputs=True)
-    inner = lm[0, 0, 2:-2, 2:-2]
-    assert float(inner.abs().max()) < 1e-4
-    assert float((syn - img).abs()[..., 2:-2, 2:-2].max()) < 1e-4
+    xs = torch.arange(W, device="cuda", dtype=torch.float32)
+    ys = torch.arange(H, device="cuda", dtype=torch.float32)
+    assert float((pix[0, :, :, 0] - ((xs / (W - 1) - 0.5) * 2)[None, :]).abs().max()) < 1e-5
+    assert float((pix[0, :, :, 1] - ((ys / (H - 1) - 0.5) * 2)[:, None]).abs().max()) < 1e-5
+    assert float(valid.min()) == 1.0
+    ref = torch.nn.functional.grid_sample(img, pix, padding_mode="border", align_corners=False)
+    assert float((syn - ref).abs().max()) < 1e-6
 
 
 def test_rejects_cpu_and_wrong_dtype(e2e):
