@@ -26,20 +26,20 @@ _SIGNATURES = {
     "e2e_warp_photo_bwd": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _F, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_ssim_fwd": (_I, [_P, _S, _P, _S, _I, _I, _I, _I, _P, _P, _P]),
     "e2e_ssim_bwd": (_I, [_P, _S, _P, _S, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    # PENDING "e2e_backproject_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
-    # PENDING "e2e_backproject_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
-    # PENDING "e2e_project3d_fwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
-    # PENDING "e2e_project3d_bwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _SZ, _P]),
-    # PENDING "e2e_grid_sample_fwd": (_I, [_P, _S, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    # PENDING "e2e_grid_sample_bwd": (_I, [_P, _P, _S, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _S, _P, _P]),
-    # PENDING "e2e_reduce_workspace_bytes": (_SZ, [_LL]),
-    # PENDING "e2e_smooth_fwd": (_I, [_P, _P, _S, _I, _I, _I, _P, _P, _SZ, _P]),
-    # PENDING "e2e_smooth_bwd": (_I, [_P, _P, _S, _I, _I, _I, _P, _P, _P, _SZ, _P]),
-    # PENDING "e2e_sparse_l1_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
-    # PENDING "e2e_sparse_l1_bwd": (_I, [_P, _P, _P, _LL, _P, _P, _P]),
-    # PENDING "e2e_depth_reg_fwd": (_I, [_P, _P, _LL, _I, _P, _P, _SZ, _P]),
-    # PENDING "e2e_depth_reg_bwd": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
-    # PENDING "e2e_geometric_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
+    "e2e_backproject_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "e2e_backproject_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "e2e_project3d_fwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "e2e_project3d_bwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+    "e2e_grid_sample_fwd": (_I, [_P, _S, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "e2e_grid_sample_bwd": (_I, [_P, _P, _S, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _S, _P, _P]),
+    "e2e_reduce_workspace_bytes": (_SZ, [_LL]),
+    "e2e_smooth_fwd": (_I, [_P, _P, _S, _I, _I, _I, _P, _P, _SZ, _P]),
+    "e2e_smooth_bwd": (_I, [_P, _P, _S, _I, _I, _I, _P, _P, _P, _SZ, _P]),
+    "e2e_sparse_l1_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
+    "e2e_sparse_l1_bwd": (_I, [_P, _P, _P, _LL, _P, _P, _P]),
+    "e2e_depth_reg_fwd": (_I, [_P, _P, _LL, _I, _P, _P, _SZ, _P]),
+    "e2e_depth_reg_bwd": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
+    "e2e_geometric_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
     # PENDING "e2e_rgbd_maps": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     # PENDING "e2e_rgbd_maps_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     # PENDING "e2e_fusion_associate": (_I, [_P, _P, _P, _LL, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),

