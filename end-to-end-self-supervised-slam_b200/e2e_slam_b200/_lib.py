@@ -40,13 +40,14 @@ _SIGNATURES = {
     "e2e_depth_reg_fwd": (_I, [_P, _P, _LL, _I, _P, _P, _SZ, _P]),
     "e2e_depth_reg_bwd": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
     "e2e_geometric_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
-    # PENDING "e2e_rgbd_maps": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
-    # PENDING "e2e_rgbd_maps_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
-    # PENDING "e2e_fusion_associate": (_I, [_P, _P, _P, _LL, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
-    # PENDING "e2e_fusion_workspace_bytes": (_SZ, [_I, _I]),
-    # PENDING "e2e_fusion_merge_append": (_I, [_P, _P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _SZ, _P]),
-    # PENDING "e2e_knn1_fwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P]),
-    # PENDING "e2e_knn1_bwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P]),
+    "e2e_rgbd_maps": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "e2e_rgbd_maps_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "e2e_fusion_associate": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P]),
+    "e2e_fusion_workspace_bytes": (_SZ, [_I, _I]),
+    "e2e_fusion_merge_append": (_I, [_P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _SZ, _P]),
+    "e2e_fusion_merge_append_bwd": (_I, [_P] * 11 + [_I, _I] + [_P] * 7),
+    "e2e_knn1_fwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P]),
+    "e2e_knn1_bwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

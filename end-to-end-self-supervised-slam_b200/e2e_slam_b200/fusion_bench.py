@@ -1,0 +1,33 @@
+"""Secondary benchmark metric (BASELINE.json config C3): PointFusion over a 60-frame synthetic RGB-D
+sequence at 480x640 with ground-truth poses; reports points fused/s = valid live pixels processed per
+second (device time, CUDA events), the final map size and kernel launches."""
+import numpy as np
+import torch
+
+
+def run(device, frames=60, H=480, W=640, repeats=3):
+    from . import ops
+    from .slam import PointFusion, RGBDImages
+    from .synthetic import room_sequence
+    depth, rgb, K, poses = room_sequence(frames, H, W, device=device)
+    rgbd = RGBDImages(rgb.unsqueeze(0), depth.unsqueeze(0).unsqueeze(-1), K.view(1, 1, 4, 4), poses.unsqueeze(0))
+    slam = PointFusion(odom="gt", dist_th=0.05, angle_th=20, sigma=0.6, device=device)
+    best, n_final, launches = None, 0, 0
+    with torch.no_grad():
+        for r in range(repeats + 1):
+            l0 = ops.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(device)
+            e0.record()
+            pc, _ = slam(rgbd)
+            e1.record()
+            torch.cuda.synchronize(device)
+            ms = e0.elapsed_time(e1)
+            if r > 0:
+                best = ms if best is None else min(best, ms)
+            launches = ops.launch_count() - l0
+            n_final = int(pc._maps[0].n_dev.item())
+    valid_px = int((depth > 0).sum().item())
+    return {"metric": "points fused/s", "value": valid_px / (best * 1e-3), "unit": "points/s", "frames": frames, "height": H, "width": W,
+            "ms_per_sequence": best, "live_points": valid_px, "final_map_points": n_final, "gpu_launches": launches,
+            "config": "C3 fusion-60: PointFusion(odom='gt', dist_th=0.05, angle_th=20, sigma=0.6), synthetic room, best of %d" % repeats}

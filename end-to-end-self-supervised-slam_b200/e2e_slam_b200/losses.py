@@ -183,3 +183,98 @@ def depth_metrics(dataset, gt, pred):
     else:
         raise ValueError("Dataset Not Found")
     return compute_depth_errors(gt[valid], pred[valid])
+
+
+# ------------------------------------------------------------------------------------------------
+# Point supervision: chamferdist.chamfer.knn_points (K = 1) and the losses built on it
+# ------------------------------------------------------------------------------------------------
+from collections import namedtuple  # noqa: E402
+
+_KNN = namedtuple("KNN", "dists idx knn")
+
+
+class _KNN1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query, ref, transform):
+        f32(query, "query points"), f32(ref, "reference points")
+        q, r = query.contiguous(), ref.contiguous()
+        t = None if transform is None else f32(transform, "transform").contiguous()
+        P1, P2 = q.shape[0], r.shape[0]
+        dist2 = torch.empty(P1, dtype=torch.float32, device=q.device)
+        idx = torch.empty(P1, dtype=torch.int64, device=q.device)
+        with torch.cuda.device(q.device):
+            check(lib().e2e_knn1_fwd(ptr(q), ptr(t), ptr(r), P1, P2, ptr(dist2), ptr(idx), stream_ptr()), "e2e_knn1_fwd")
+        ctx.save_for_backward(q, r, idx) if t is None else ctx.save_for_backward(q, r, idx, t)
+        ctx.mark_non_differentiable(idx)
+        return dist2, idx
+
+    @staticmethod
+    def backward(ctx, g, _):
+        saved = ctx.saved_tensors
+        q, r, idx = saved[:3]
+        t = saved[3] if len(saved) > 3 else None
+        g = f32(g, "grad").contiguous()
+        gq = torch.empty_like(q) if ctx.needs_input_grad[0] else None
+        gr = torch.zeros_like(r) if ctx.needs_input_grad[1] else None
+        if gq is None and gr is None:
+            return None, None, None
+        with torch.cuda.device(q.device):
+            check(lib().e2e_knn1_bwd(ptr(q), ptr(t), ptr(r), q.shape[0], r.shape[0], ptr(idx), ptr(g), ptr(gq), ptr(gr), stream_ptr()),
+                  "e2e_knn1_bwd")
+        return gq, gr, None
+
+
+def knn_points(p1, p2, lengths1=None, lengths2=None, K=1, version=-1, return_nn=False, return_sorted=True):
+    """chamferdist.chamfer.knn_points for K = 1: for every point of p1 (N,P1,3) the squared distance to and
+    the index of its nearest neighbour in p2 (N,P2,3).  Returns KNN(dists (N,P1,1), idx (N,P1,1), knn=None)."""
+    if K != 1 or lengths1 is not None or lengths2 is not None or return_nn:
+        raise NotImplementedError("only K = 1 on full clouds is used by the reference (loss/losses.py:57)")
+    if p1.dim() != 3 or p2.dim() != 3 or p1.shape[2] != 3 or p2.shape[2] != 3:
+        raise ValueError(f"expected (N,P,3) point clouds, got {tuple(p1.shape)} / {tuple(p2.shape)}")
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    d, i = zip(*[_KNN1.apply(p1[b], p2[b], None) for b in range(p1.shape[0])])
+    return _KNN(dists=torch.stack(d).unsqueeze(-1), idx=torch.stack(i).unsqueeze(-1), knn=None)
+
+
+def knn_points_loss(gt_pointcloud, noisy_pointcloud):
+    """Mean squared distance from every noisy point to its nearest ground-truth point, and the indices
+    (loss/losses.py:39-63).  Same argument order and errors as the reference."""
+    if gt_pointcloud.shape[0] != noisy_pointcloud.shape[0]:
+        raise ValueError("Pointclouds must have the same batch dimension")
+    if gt_pointcloud.shape[2] != noisy_pointcloud.shape[2]:
+        raise ValueError("Number of axes is not the same in both pointclouds")
+    KNN = knn_points(noisy_pointcloud, gt_pointcloud)
+    distances = KNN.dists.squeeze(-1)
+    indexes = KNN.idx.squeeze(-1).detach()
+    return torch.mean(distances), indexes
+
+
+def color_points_loss(gt_pointcloud_color, noisy_pointcloud_color, indexes):
+    """L1 between each noisy point's colour and the colour of its matched ground-truth point
+    (loss/losses.py:65-82); a gather + mean on the GPU."""
+    if gt_pointcloud_color.shape[2] != noisy_pointcloud_color.shape[2]:
+        raise ValueError("Number of axes is not the same in both pointclouds")
+    return torch.mean(torch.abs(noisy_pointcloud_color[0] - gt_pointcloud_color[0, indexes[0].long()]))
+
+
+def point_supervision_loss(target_points, transform, global_points):
+    """compute_3d_loss (online_adaption.py:638-645) with transform_pointcloud fused into the kernel's query
+    load: mean squared distance of R p + t (p in target_points (N,3)) to the nearest of global_points (M,3),
+    which is treated as constant like the reference's `.detach()`."""
+    d, _ = _KNN1.apply(target_points, global_points.detach(), transform)
+    return d.mean()
+
+
+class ChamferDistance(nn.Module):
+    """chamferdist.ChamferDistance, forward direction plus optional reverse (train_depth.py:689-695)."""
+
+    def forward(self, source_cloud, target_cloud, bidirectional=False, reverse=False, reduction="mean"):
+        if reduction not in ("mean", "sum"):
+            raise ValueError('reduction must be "mean" or "sum"')
+        red = (lambda t: t.mean(1).mean()) if reduction == "mean" else (lambda t: t.sum())
+        fwd = red(knn_points(source_cloud, target_cloud).dists.squeeze(-1))
+        if not (bidirectional or reverse):
+            return fwd
+        bwd = red(knn_points(target_cloud, source_cloud).dists.squeeze(-1))
+        return fwd + bwd if bidirectional else bwd

@@ -1,0 +1,392 @@
+"""gradslam-compatible surface for the part of gradslam the reference drives:
+`RGBDImages`, `Pointclouds`, `PointFusion` (.step / __call__), `transform_pointcloud`, plus the reference's own
+`image_recover_slam` (slam/custom_slam.py:6-35).  Only the attributes the reference touches are provided:
+    RGBDImages(rgb_image, depth_image, intrinsics, poses)[:, s] / .to / .detach / .shape / .poses (settable) /
+        .rgb_image / .depth_image / .intrinsics
+    Pointclouds(device=).points_list / .colors_list / .normals_list / .features_list / .has_points / .detach() /
+        [b] / len()
+    PointFusion(odom=, dist_th=, angle_th=, sigma=, numiters=, device=).step(pointclouds, live_frame,
+        prev_frame=None, inplace=False) -> (pointclouds, poses);  slam(frames) -> (pointclouds, poses)
+Fusion semantics are those of oracle/fusion_oracle.py (gradslam as restated in SURVEY.md appendix B).
+The map size lives on the device; a step launches 7 kernels and never synchronises with the host.
+Reading `points_list` does (it has to know N).
+
+Odometry: PointFusion.step localises with the frame's own pose when `odom == "gt"` or `prev_frame is None`
+-- exactly gradslam's rule.  ICP / GradICP odometry is not part of this
+round; asking for it raises NotImplementedError instead of silently using another pose.
+"""
+import ctypes
+import math
+
+import torch
+
+from ._lib import check, f32, lib, ptr, stream_ptr
+
+
+class RGBDImages:
+    """Channels-last RGB-D sequence container: rgb (B,L,H,W,3), depth (B,L,H,W,1), intrinsics (B,1,4,4),
+    poses (B,L,4,4) camera->world (may be None)."""
+
+    def __init__(self, rgb_image, depth_image, intrinsics, poses=None, channels_first=False, device=None):
+        for name, t, nd in (("rgb_image", rgb_image, 5), ("depth_image", depth_image, 5), ("intrinsics", intrinsics, 4)):
+            if not torch.is_tensor(t):
+                raise TypeError(f"Expected {name} to be of type tensor. Got {type(t)}.")
+            if t.dim() != nd:
+                raise ValueError(f"{name} should have {nd} dimensions. Got {t.dim()}.")
+        if channels_first:
+            rgb_image, depth_image = rgb_image.permute(0, 1, 3, 4, 2), depth_image.permute(0, 1, 3, 4, 2)
+        if rgb_image.shape[:4] != depth_image.shape[:4] or rgb_image.shape[-1] != 3 or depth_image.shape[-1] != 1:
+            raise ValueError(f"rgb_image {tuple(rgb_image.shape)} and depth_image {tuple(depth_image.shape)} are inconsistent")
+        if intrinsics.shape != (rgb_image.shape[0], 1, 4, 4):
+            raise ValueError(f"intrinsics should be ({rgb_image.shape[0]},1,4,4). Got {tuple(intrinsics.shape)}.")
+        if poses is not None and (not torch.is_tensor(poses) or poses.shape != (*rgb_image.shape[:2], 4, 4)):
+            raise ValueError(f"poses should be {(*rgb_image.shape[:2], 4, 4)}")
+        self._rgb, self._depth, self._K, self._poses = rgb_image, depth_image, intrinsics, poses
+        if device is not None:
+            self.to(device)
+
+    rgb_image = property(lambda self: self._rgb)
+    depth_image = property(lambda self: self._depth)
+    intrinsics = property(lambda self: self._K)
+    device = property(lambda self: self._rgb.device)
+
+    @property
+    def poses(self):
+        return self._poses
+
+    @poses.setter
+    def poses(self, value):
+        if value is not None and (not torch.is_tensor(value) or value.shape != (*self._rgb.shape[:2], 4, 4)):
+            raise ValueError(f"poses should be {(*self._rgb.shape[:2], 4, 4)}")
+        self._poses = value
+
+    @property
+    def shape(self):
+        return tuple(self._rgb.shape[:4])
+
+    def __len__(self):
+        return self._rgb.shape[0]
+
+    def __getitem__(self, index):
+        if not isinstance(index, tuple):
+            index = (index,)
+        if len(index) > 2:
+            raise IndexError("RGBDImages supports indexing of the batch and sequence dimensions only")
+        keep = tuple(slice(i, i + 1) if isinstance(i, int) else i for i in index)      # ints keep their dimension
+        bidx = keep[0]
+        return RGBDImages(self._rgb[keep], self._depth[keep], self._K[bidx],
+                          None if self._poses is None else self._poses[keep])
+
+    def to(self, device):
+        self._rgb, self._depth, self._K = self._rgb.to(device), self._depth.to(device), self._K.to(device)
+        if self._poses is not None:
+            self._poses = self._poses.to(device)
+        return self
+
+    def detach(self):
+        return RGBDImages(self._rgb.detach(), self._depth.detach(), self._K.detach(),
+                          None if self._poses is None else self._poses.detach())
+
+    def clone(self):
+        return RGBDImages(self._rgb.clone(), self._depth.clone(), self._K.clone(),
+                          None if self._poses is None else self._poses.clone())
+
+    def plotly(self, *a, **k):
+        raise NotImplementedError("visualisation is out of scope (plotly is not a dependency of this package)")
+
+
+class _Map:
+    """One batch element's map: structure of arrays with spare capacity; N lives on the device."""
+
+    __slots__ = ("pts", "nrm", "col", "cc", "n_dev", "n_upper", "n_host")
+
+    def __init__(self, device):
+        z = dict(dtype=torch.float32, device=device)
+        self.pts, self.nrm, self.col = torch.empty(0, 3, **z), torch.empty(0, 3, **z), torch.empty(0, 3, **z)
+        self.cc = torch.empty(0, **z)
+        self.n_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.n_upper = 0       # host-side upper bound of N (sizes grids; tightened when N is read)
+        self.n_host = 0        # last N seen by the host (exact only right after count())
+
+    def count(self):
+        self.n_host = int(self.n_dev.item())       # the one place the host synchronises
+        self.n_upper = self.n_host
+        return self.n_host
+
+    def copy(self, detach=False):
+        m = _Map(self.pts.device)
+        f = (lambda t: t.detach()) if detach else (lambda t: t)
+        m.pts, m.nrm, m.col, m.cc = f(self.pts), f(self.nrm), f(self.col), f(self.cc)
+        m.n_dev, m.n_upper, m.n_host = self.n_dev, self.n_upper, self.n_host
+        return m
+
+
+class Pointclouds:
+    """Batch of point clouds with per-point normals, colours and a scalar feature (PointFusion's confidence
+    count).  Lists may be given at construction (gradslam-style) or the object starts empty."""
+
+    def __init__(self, points=None, normals=None, colors=None, features=None, device=None):
+        self.device = torch.device(device) if device is not None else (points[0].device if points else torch.device("cuda"))
+        self._maps = []
+        if points is not None:
+            for b, p in enumerate(points):
+                m = _Map(self.device)
+                n = p.shape[0]
+                m.pts = f32(p.to(self.device), "points").contiguous()
+                m.nrm = normals[b].to(self.device).contiguous() if normals is not None else torch.zeros_like(m.pts)
+                m.col = colors[b].to(self.device).contiguous() if colors is not None else torch.zeros_like(m.pts)
+                m.cc = (features[b].to(self.device).reshape(-1).contiguous() if features is not None
+                        else torch.ones(n, dtype=torch.float32, device=self.device))
+                m.n_dev = torch.full((1,), n, dtype=torch.int64, device=self.device)
+                m.n_upper = m.n_host = n
+                self._maps.append(m)
+
+    def __len__(self):
+        return len(self._maps)
+
+    @property
+    def has_points(self):
+        return any(m.n_upper > 0 for m in self._maps)
+
+    def _list(self, attr):
+        out = []
+        for m in self._maps:
+            n = m.count()
+            out.append(getattr(m, attr)[:n])
+        return out
+
+    points_list = property(lambda self: self._list("pts"))
+    normals_list = property(lambda self: self._list("nrm"))
+    colors_list = property(lambda self: self._list("col"))
+    features_list = property(lambda self: [c.unsqueeze(-1) for c in self._list("cc")])
+
+    @property
+    def num_points_per_pointcloud(self):
+        return torch.tensor([m.count() for m in self._maps], dtype=torch.int64)
+
+    def __getitem__(self, b):
+        pc = Pointclouds(device=self.device)
+        pc._maps = [self._maps[b]] if isinstance(b, int) else self._maps[b]
+        return pc
+
+    def detach(self):
+        pc = Pointclouds(device=self.device)
+        pc._maps = [m.copy(detach=True) for m in self._maps]
+        return pc
+
+    def clone(self):
+        pc = Pointclouds(device=self.device)
+        for m in self._maps:
+            c = m.copy()
+            c.pts, c.nrm, c.col, c.cc, c.n_dev = m.pts.clone(), m.nrm.clone(), m.col.clone(), m.cc.clone(), m.n_dev.clone()
+            pc._maps.append(c)
+        return pc
+
+    def to(self, device):
+        if torch.device(device) != self.device:
+            raise NotImplementedError("Pointclouds live on the device they were created on")
+        return self
+
+    def plotly(self, *a, **k):
+        raise NotImplementedError("visualisation is out of scope (plotly is not a dependency of this package)")
+
+
+def _frame_maps(depth, K, pose, sigma):
+    """vertex_g, normal_g [H,W,3], alpha [H,W], valid [H,W] uint8 of one frame (e2e_rgbd_maps)."""
+    H, W = depth.shape
+    dev = depth.device
+    vg = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    ng = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    alpha = torch.empty(H, W, dtype=torch.float32, device=dev)
+    valid = torch.empty(H, W, dtype=torch.uint8, device=dev)
+    check(lib().e2e_rgbd_maps(ptr(depth), None, ptr(K), ptr(pose), H, W, ctypes.c_float(sigma), ptr(vg), ptr(ng), ptr(alpha),
+                              ptr(valid), stream_ptr()), "e2e_rgbd_maps")
+    return vg, ng, alpha, valid
+
+
+class _FusionStep(torch.autograd.Function):
+    """One update_map_fusion for one batch element.  Returns new (points, normals, colors, ccount, n_dev,
+    index_map, append_slot); the buffers have spare capacity, N is n_dev."""
+
+    @staticmethod
+    def forward(ctx, depth, rgb, K, pose, old_pts, old_nrm, old_col, old_cc, n_dev, n_upper, dist_th, dot_th, sigma, in_place):
+        H, W = depth.shape
+        dev = depth.device
+        with torch.cuda.device(dev):
+            vg, ng, alpha, valid = _frame_maps(depth, K, pose, sigma)
+            keys = torch.empty(H, W, dtype=torch.int64, device=dev)
+            index_map = torch.empty(H, W, dtype=torch.int64, device=dev)
+            check(lib().e2e_fusion_associate(ptr(old_pts), ptr(old_nrm), ptr(old_cc), ptr(n_dev), n_upper, ptr(K), ptr(pose),
+                                             ptr(vg), ptr(ng), H, W, ctypes.c_float(dist_th), ctypes.c_float(dot_th),
+                                             ptr(keys), ptr(index_map), stream_ptr()), "e2e_fusion_associate")
+            need = n_upper + H * W
+            cap_old = old_pts.shape[0]
+            if in_place and cap_old >= need:
+                pts, nrm, col, cc = old_pts, old_nrm, old_col, old_cc
+            else:
+                cap = max(need, int(1.5 * cap_old)) if in_place else need
+                z = dict(dtype=torch.float32, device=dev)
+                pts, nrm, col, cc = torch.empty(cap, 3, **z), torch.empty(cap, 3, **z), torch.empty(cap, 3, **z), torch.empty(cap, **z)
+                k = min(n_upper, cap_old)
+                pts[:k], nrm[:k], col[:k], cc[:k] = old_pts[:k], old_nrm[:k], old_col[:k], old_cc[:k]
+            append_slot = torch.empty(H, W, dtype=torch.int64, device=dev)
+            n_out = torch.empty(1, dtype=torch.int64, device=dev)
+            nws = lib().e2e_fusion_workspace_bytes(H, W)
+            ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+            check(lib().e2e_fusion_merge_append(ptr(pts), ptr(nrm), ptr(col), ptr(cc), ptr(n_dev), pts.shape[0], ptr(vg), ptr(ng),
+                                                ptr(rgb), ptr(alpha), ptr(valid), ptr(index_map), H, W, ptr(append_slot),
+                                                ptr(n_out), ptr(ws), nws, stream_ptr()), "e2e_fusion_merge_append")
+        ctx.save_for_backward(depth, K, pose, old_pts, old_col, old_cc, vg, rgb, alpha, index_map, append_slot)
+        ctx.sigma = sigma
+        ctx.mark_non_differentiable(nrm, n_out, index_map, append_slot)
+        if in_place and pts is old_pts:
+            ctx.mark_dirty(old_pts, old_nrm, old_col, old_cc)
+        return pts, nrm, col, cc, n_out, index_map, append_slot
+
+    @staticmethod
+    def backward(ctx, g_pts, g_nrm, g_col, g_cc, *_):
+        depth, K, pose, old_pts, old_col, old_cc, vg, rgb, alpha, index_map, append_slot = ctx.saved_tensors
+        H, W = depth.shape
+        dev = depth.device
+        z = dict(dtype=torch.float32, device=dev)
+        g_vg, g_rgb, g_alpha = torch.empty(H, W, 3, **z), torch.empty(H, W, 3, **z), torch.empty(H, W, **z)
+        cap_old = old_pts.shape[0]
+        need_old = any(ctx.needs_input_grad[i] for i in (4, 6, 7)) and cap_old > 0
+
+        def passthrough(g, shape):
+            if not need_old:
+                return None
+            return g[:cap_old].clone() if g is not None else torch.zeros(shape, **z)
+
+        go_pts, go_col, go_cc = passthrough(g_pts, (cap_old, 3)), passthrough(g_col, (cap_old, 3)), passthrough(g_cc, (cap_old,))
+        c = lambda t: None if t is None else t.contiguous()
+        with torch.cuda.device(dev):
+            check(lib().e2e_fusion_merge_append_bwd(ptr(c(g_pts)), ptr(c(g_col)), ptr(c(g_cc)), ptr(old_pts), ptr(old_col), ptr(old_cc),
+                                                    ptr(vg), ptr(rgb), ptr(alpha), ptr(index_map), ptr(append_slot), H, W,
+                                                    ptr(g_vg), ptr(g_rgb), ptr(g_alpha), ptr(go_pts), ptr(go_col), ptr(go_cc),
+                                                    stream_ptr()), "e2e_fusion_merge_append_bwd")
+            g_depth = None
+            if ctx.needs_input_grad[0]:
+                g_depth = torch.empty(H, W, **z)
+                check(lib().e2e_rgbd_maps_bwd(ptr(depth), ptr(K), ptr(pose), H, W, ctypes.c_float(ctx.sigma), ptr(g_vg), None,
+                                              ptr(g_alpha), ptr(g_depth), stream_ptr()), "e2e_rgbd_maps_bwd")
+        return (g_depth, g_rgb if ctx.needs_input_grad[1] else None, None, None, go_pts, None, go_col, go_cc,
+                None, None, None, None, None, None)
+
+
+class PointFusion:
+    """Point-based fusion SLAM (gradslam.slam.PointFusion as driven by the reference: constructor arguments
+    at train_depth.py:111-118, .step at slam/custom_slam.py:33 and online_adaption.py:354-363, 466-469,
+    __call__ at train_depth.py:266, 378-381)."""
+
+    def __init__(self, odom="gradicp", dist_th=0.05, angle_th=20, sigma=0.6, dsratio=4, numiters=20, damp=1e-8,
+                 dist_thresh=None, lambda_max=2.0, B=1.0, B2=1.0, nu=200.0, device=None):
+        if odom not in ("gt", "icp", "gradicp"):
+            raise ValueError(f"odometry method ({odom}) not supported for PointFusion")
+        for name, v in (("dist_th", dist_th), ("angle_th", angle_th), ("sigma", sigma)):
+            if not isinstance(v, (int, float)):
+                raise TypeError(f"{name} must be a number. Got {type(v)}.")
+        if dist_th < 0 or not (0 <= angle_th <= 90):
+            raise ValueError("dist_th must be non-negative and angle_th within [0, 90]")
+        self.odom, self.dist_th, self.angle_th, self.sigma = odom, float(dist_th), float(angle_th), float(sigma)
+        self.dot_th = math.cos(angle_th * math.pi / 180.0)
+        self.numiters, self.dsratio = numiters, dsratio
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.last_association = None      # index_map / append_slot of the most recent step (tests, debugging)
+
+    def _localize(self, live_frame, prev_frame):
+        if self.odom == "gt" or prev_frame is None:
+            if live_frame.poses is None:
+                raise ValueError("live_frame.poses must be set when odom == 'gt' or prev_frame is None")
+            return live_frame.poses
+        raise NotImplementedError(
+            f"odom={self.odom!r} (ICP / GradICP odometry) is not implemented in this round (SURVEY.md section 8(f)); "
+            "construct PointFusion(odom='gt') -- the reference's own GT_SLAM (train_depth.py:118) -- or pass prev_frame=None")
+
+    def step(self, pointclouds, live_frame, prev_frame=None, inplace=False):
+        if not isinstance(pointclouds, Pointclouds):
+            raise TypeError(f"Expected pointclouds to be of type Pointclouds. Got {type(pointclouds)}.")
+        if not isinstance(live_frame, RGBDImages):
+            raise TypeError(f"Expected live_frame to be of type RGBDImages. Got {type(live_frame)}.")
+        if live_frame.shape[1] != 1:
+            raise ValueError(f"live_frame must have sequence length 1. Got {live_frame.shape[1]}.")
+        poses = self._localize(live_frame, prev_frame)
+        live_frame.poses = poses
+        B, _, H, W = live_frame.shape
+        if len(pointclouds) not in (0, B):
+            raise ValueError(f"pointclouds batch size ({len(pointclouds)}) does not match the frame's ({B})")
+        out = pointclouds if inplace else Pointclouds(device=pointclouds.device)
+        maps = []
+        self.last_association = []
+        for b in range(B):
+            old = pointclouds._maps[b] if len(pointclouds) else _Map(live_frame.device)
+            depth = f32(live_frame.depth_image[b, 0, :, :, 0], "depth_image").contiguous()
+            rgb = f32(live_frame.rgb_image[b, 0], "rgb_image").contiguous()
+            K = f32(live_frame.intrinsics[b, 0], "intrinsics").contiguous()
+            pose = f32(poses[b, 0], "poses").detach().contiguous()
+            if old.n_upper > 4 * H * W + 2 * old.n_host:
+                old.count()                     # occasionally tighten the bound (one sync) so buffers stay compact
+            grad = torch.is_grad_enabled() and (depth.requires_grad or rgb.requires_grad or old.pts.requires_grad or
+                                                old.col.requires_grad or old.cc.requires_grad)
+            pts, nrm, col, cc, n_out, index_map, slot = _FusionStep.apply(
+                depth, rgb, K, pose, old.pts, old.nrm, old.col, old.cc, old.n_dev, old.n_upper,
+                self.dist_th, self.dot_th, self.sigma, bool(inplace and not grad))
+            m = old if inplace else _Map(live_frame.device)
+            m.pts, m.nrm, m.col, m.cc, m.n_dev = pts, nrm, col, cc, n_out
+            m.n_upper, m.n_host = old.n_upper + H * W, old.n_host
+            maps.append(m)
+            self.last_association.append((index_map, slot))
+        out._maps = maps
+        return out, poses
+
+    def forward(self, frames):
+        if not isinstance(frames, RGBDImages):
+            raise TypeError(f"Expected frames to be of type RGBDImages. Got {type(frames)}.")
+        pointclouds = Pointclouds(device=frames.device)
+        B, L = frames.shape[:2]
+        prev, recovered = None, []
+        for s in range(L):
+            live = frames[:, s]
+            if s == 0 and live.poses is None:
+                live.poses = torch.eye(4, device=frames.device).view(1, 1, 4, 4).repeat(B, 1, 1, 1)
+            pointclouds, pose = self.step(pointclouds, live, prev, inplace=True)
+            prev = live if self.odom != "gt" else None
+            recovered.append(pose)
+        return pointclouds, torch.cat(recovered, 1)
+
+    __call__ = forward
+
+
+class ICPSLAM(PointFusion):
+    """Placeholder for gradslam.slam.ICPSLAM (imported by the reference, selected only by MODEL.slam ==
+    'ICPSLAM'): its map update is plain concatenation, which is out of this round's scope."""
+
+    def step(self, *a, **k):
+        raise NotImplementedError("ICPSLAM is out of scope; use PointFusion (configs/config.yaml:29)")
+
+
+def transform_pointcloud(pointcloud, transform):
+    """gradslam.geometry.geometryutils.transform_pointcloud: (N,3) points by a 4x4 rigid transform
+    (online_adaption.py:642).  A 3x3 rotate-and-add; `losses.point_supervision_loss` fuses it into the
+    nearest-neighbour kernel's query load instead."""
+    if not torch.is_tensor(pointcloud) or not torch.is_tensor(transform):
+        raise TypeError("pointcloud and transform must be tensors")
+    if pointcloud.dim() != 2 or pointcloud.shape[1] != 3 or transform.shape != (4, 4):
+        raise ValueError(f"expected pointcloud (N,3) and transform (4,4), got {tuple(pointcloud.shape)} / {tuple(transform.shape)}")
+    return pointcloud @ transform[:3, :3].t() + transform[:3, 3]
+
+
+def image_recover_slam(noisy_rgbd, slam, device):
+    """slam/custom_slam.py:6-35: fuse a sequence frame by frame, detaching every frame but the last, so the
+    gradient reaches only the last frame's depth and colour."""
+    noisy_pointcloud = Pointclouds(device=device)
+    batch_size, seq_len = noisy_rgbd.shape[:2]
+    initial_poses = torch.eye(4, device=device).view(1, 1, 4, 4).repeat(batch_size, 1, 1, 1)
+    for s in range(seq_len):
+        live_frame = noisy_rgbd[:, s].to(device)
+        live_frame = live_frame.detach() if s < seq_len - 1 else live_frame
+        if s == 0 and live_frame.poses is None:
+            live_frame.poses = initial_poses
+        noisy_pointcloud, live_frame.poses = slam.step(noisy_pointcloud, live_frame)
+        live_frame.poses = live_frame.poses.detach()
+    return noisy_pointcloud

@@ -70,3 +70,44 @@ def make_pairs(B, H, W, kind="icl", seed=0, device="cpu", rot_deg=2.0, trans=0.0
     inv_K = torch.pinverse(K)      # train_depth.py:460-461
     return dict(depth=depth.unsqueeze(1).contiguous().to(device), K=K.to(device), inv_K=inv_K.to(device),
                 T=T.to(device), colors=colors.contiguous().to(device))
+
+
+def room_sequence(L, H, W, device="cpu", seed=0):
+    """Config C3: an analytic box room ray-cast to L depth + colour frames along a smooth trajectory with
+    ground-truth poses (2-3 cm and ~0.6 degrees per frame).  Returns depth (L,H,W), rgb (L,H,W,3), K (4,4),
+    poses (L,4,4) on `device`."""
+    device = torch.device(device)
+    g = torch.Generator().manual_seed(seed)
+    fx = fy = 525.0 * W / 640.0
+    cx, cy = W / 2 - 0.5, H / 2 - 0.5
+    K = torch.eye(4)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = fx, fy, cx, cy
+    half = torch.tensor([2.0, 1.4, 3.5], dtype=torch.float64, device=device)
+    vv, uu = torch.meshgrid(torch.arange(H, dtype=torch.float64, device=device), torch.arange(W, dtype=torch.float64, device=device),
+                            indexing="ij")
+    rays = torch.stack([(uu - cx) / fx, (vv - cy) / fy, torch.ones_like(uu)], -1)
+    depth = torch.empty(L, H, W, device=device)
+    rgb = torch.empty(L, H, W, 3, device=device)
+    poses = torch.empty(L, 4, 4)
+    pos = torch.tensor([0.1, -0.1, 0.0], dtype=torch.float64)
+    yaw = pitch = 0.0
+    for s in range(L):
+        cyw, syw, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+        Ry = torch.tensor([[cyw, 0, syw], [0, 1, 0], [-syw, 0, cyw]], dtype=torch.float64)
+        Rx = torch.tensor([[1, 0, 0], [0, cp, -sp], [0, sp, cp]], dtype=torch.float64)
+        R = Ry @ Rx
+        dirs = rays @ R.t().to(device)
+        p = pos.to(device)
+        tt = torch.where(dirs > 0, (half - p) / dirs, (-half - p) / dirs)
+        tt = torch.where(torch.isfinite(tt) & (tt > 0), tt, torch.full_like(tt, float("inf")))
+        thit, wall = tt.min(-1)
+        hit = p + dirs * thit.unsqueeze(-1)
+        depth[s] = thit.float()
+        tex = 0.5 + 0.25 * torch.sin(3.0 * hit[..., 0] + wall) + 0.25 * torch.cos(2.5 * hit[..., 1] + 1.3 * hit[..., 2])
+        rgb[s] = torch.stack([tex, 0.8 * tex + 0.1 * torch.sin(hit[..., 2]), 1.0 - tex], -1).clamp(0, 1).float()
+        poses[s] = torch.eye(4)
+        poses[s, :3, :3], poses[s, :3, 3] = R.float(), pos.float()
+        pos = pos + torch.tensor([0.02, 0.003, 0.015], dtype=torch.float64) + 0.002 * torch.randn(3, generator=g, dtype=torch.float64)
+        yaw += math.radians(0.6)
+        pitch += math.radians(0.1) * math.sin(s / 5.0)
+    return depth, rgb, K.to(device), poses.to(device)

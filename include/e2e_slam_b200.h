@@ -160,7 +160,8 @@ int e2e_geometric_fwd(const float *warped_depth, const float *interp_depth, cons
  *                         Outputs vertex_g, normal_g [H,W,3], alpha [H,W], valid [H,W] (uint8).
  *   e2e_fusion_associate  find_active_map_points + find_similar_map_points + find_best_unique_correspondences:
  *                         writes index_map [H,W] int64 (map point matched to each live pixel, -1 = none).
- *                         `keys` is an [H,W] uint64 scratch image.
+ *                         `keys` is an [H,W] uint64 scratch image.  The map size is read from the DEVICE
+ *                         int64 `n_map` (no host sync per step); `n_upper` >= *n_map only sizes the grid.
  *   e2e_fusion_merge_append fuse_with_map: confidence-weighted merge of matched map points in place, then
  *                         stream-compacted append (row-major pixel order) of valid unmatched live pixels at
  *                         map[n_map ...].  `n_out` (device int64[1]) receives the new point count;
@@ -174,19 +175,31 @@ int e2e_rgbd_maps_bwd(const float *depth, const float *K, const float *pose, int
                       const float *grad_vertex_g, const float *grad_normal_g, const float *grad_alpha,
                       float *grad_depth, void *stream);
 
-int e2e_fusion_associate(const float *map_points, const float *map_normals, const float *map_ccount, long long n_map,
+int e2e_fusion_associate(const float *map_points, const float *map_normals, const float *map_ccount,
+                         const long long *n_map, long long n_upper,
                          const float *K, const float *pose, const float *vertex_g, const float *normal_g,
-                         const unsigned char *valid, int H, int W, float dist_th, float dot_th,
+                         int H, int W, float dist_th, float dot_th,
                          unsigned long long *keys, long long *index_map, void *stream);
 
 size_t e2e_fusion_workspace_bytes(int H, int W);
 
 int e2e_fusion_merge_append(float *map_points, float *map_normals, float *map_colors, float *map_ccount,
-                            long long n_map, long long capacity,
+                            const long long *n_map, long long capacity,
                             const float *vertex_g, const float *normal_g, const float *rgb, const float *alpha,
                             const unsigned char *valid, const long long *index_map, int H, int W,
                             long long *append_slot, long long *n_out,
                             void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of merge + append: gradients w.r.t. the NEW map (points, colors, ccount; any may be NULL) are
+ * routed to the live frame (grad_vertex_g, grad_rgb [H,W,3], grad_alpha [H,W], written) and, for matched
+ * points, to the map that entered the step (grad_old_*; the caller pre-fills them with the pass-through
+ * gradient of the unmatched points; NULL to skip).  Normals are not differentiated. */
+int e2e_fusion_merge_append_bwd(const float *grad_points, const float *grad_colors, const float *grad_ccount,
+                                const float *old_points, const float *old_colors, const float *old_ccount,
+                                const float *vertex_g, const float *rgb, const float *alpha,
+                                const long long *index_map, const long long *append_slot, int H, int W,
+                                float *grad_vertex_g, float *grad_rgb, float *grad_alpha,
+                                float *grad_old_points, float *grad_old_colors, float *grad_old_ccount, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K = 1 nearest neighbour (chamferdist.chamfer.knn_points as used by knn_points_loss,
