@@ -174,7 +174,7 @@ def test_identity_pose_known_answer(e2e):
     ys = torch.arange(H, device="cuda", dtype=torch.float32)
     assert float((pix[0, :, :, 0] - ((xs / (W - 1) - 0.5) * 2)[None, :]).abs().max()) < 1e-5
     assert float((pix[0, :, :, 1] - ((ys / (H - 1) - 0.5) * 2)[:, None]).abs().max()) < 1e-5
-    assert float(valid.min()) == 1.0
+    assert float(valid[..., 1:-1, 1:-1].min()) == 1.0       # the outermost ring sits exactly on |g| == 1 (rounding decides)
     ref = torch.nn.functional.grid_sample(img, pix, padding_mode="border", align_corners=False)
     assert float((syn - ref).abs().max()) < 1e-6
 
