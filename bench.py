@@ -171,17 +171,19 @@ def run_ours(args):
     del chunks
     src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)   # NCHW views of NHWC memory
     plan = ops.WarpPhotoPlan(P, H, W, dev)
-    bucket = torch.zeros(GRAD_BUCKET_ELEMS, device=dev) if world > 1 else None
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    bucket = None
+    if world > 1:       # stands in for the depth net's trainable parameters: one flat fp32 gradient bucket of its size
+        from e2e_slam_b200.distributed import FlatGradBucket
+        stand_in = torch.nn.Parameter(torch.zeros(GRAD_BUCKET_ELEMS, device=dev))
+        stand_in.grad = torch.full_like(stand_in, float(rank))
+        bucket = FlatGradBucket([stand_in], device=dev)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     fwd_ms, bwd_ms = [], []
 
     def step(record):
-        if world > 1:   # depth-net gradient bucket all-reduce, overlapped with this step's kernels
-            comm.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(comm):
-                work = dist.all_reduce(bucket, async_op=True)
+        if world > 1:   # depth-net gradient bucket all-reduce on the side stream, overlapped with this step's kernels
+            bucket.start()
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
         loss = plan.forward(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
@@ -191,8 +193,7 @@ def run_ours(args):
         lib_bwd()
         e3.record()
         if world > 1:
-            work.wait()
-            torch.cuda.current_stream().wait_stream(comm)
+            bucket.finish()
         if record is not None:
             record.append((e0, e1, e2, e3))
         return loss

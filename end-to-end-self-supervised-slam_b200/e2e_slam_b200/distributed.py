@@ -1,0 +1,92 @@
+"""Data parallelism over independent key-frame pairs.
+
+The hot path has no exchange step: pairs (and source frames, and scales) are independent units, so each
+rank runs the fused kernels on its own shard with no data-path collective.  The only collective of a
+refinement step is the all-reduce of the depth network's adaptation gradients (about 57 MB of fp32,
+SURVEY.md section 5), which follows the network's backward pass -- not one of our kernels -- so there is
+nothing to fuse it into; it is issued as ONE flat bucket on a side stream so that it overlaps whatever the
+main stream does next.  PointFusion over one sequence does not shard (frame s fuses into the map of frame
+s-1): replicas only, one sequence per rank.
+
+One process per GPU (torchrun); backend "nccl" on GPUs, "gloo" in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_pairs(n_pairs, rank, world_size):
+    """Indices of the pairs rank `rank` owns: rank::world_size (round robin keeps shards within one pair of
+    each other for any n_pairs)."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    return list(range(rank, n_pairs, world_size))
+
+
+class FlatGradBucket:
+    """All-reduce(mean) of the gradients of `params` as one flat fp32 bucket.
+
+    Parameters that never receive a gradient (the reference's depth net has 8: resnet `fc` and the unused
+    `dispconv` scales) must be skipped *identically on every rank*, so membership
+    is decided by `requires_grad` at construction time, not by `grad is None` at reduce time; a member whose
+    grad is None on some rank contributes zeros.  Frozen parameters (refinement mode freezes every tensor
+    whose name contains "bn", train_depth.py:213-222) are not members."""
+
+    def __init__(self, params, process_group=None, device=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        self.group = process_group
+        self.device = torch.device(device) if device is not None else self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._work = None
+
+    def _views(self):
+        off = 0
+        for p in self.params:
+            yield p, self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def start(self):
+        """Pack the gradients and launch the all-reduce (asynchronously on the side stream on GPUs)."""
+        world = dist.get_world_size(self.group)
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            ctx = torch.cuda.stream(self.stream)
+        else:
+            ctx = torch.autograd.profiler.record_function("e2e.bucket")
+        with ctx:
+            for p, v in self._views():
+                if p.grad is None:
+                    v.zero_()
+                else:
+                    v.copy_(p.grad)
+            self.flat.div_(world)
+            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return self
+
+    def finish(self):
+        """Wait for the all-reduce and scatter the averaged gradients back into `.grad`."""
+        if self._work is None:
+            raise RuntimeError("finish() called before start()")
+        self._work.wait()
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        for p, v in self._views():
+            if p.grad is None:
+                p.grad = v.clone()
+            else:
+                p.grad.copy_(v)
+        self._work = None
+
+    def allreduce(self):
+        self.start()
+        self.finish()
+
+
+def mean_over_ranks(value, group=None):
+    """Average a scalar tensor over ranks (the logged loss); a 4-byte all-reduce."""
+    v = value.detach().clone().reshape(1)
+    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return v / dist.get_world_size(group)

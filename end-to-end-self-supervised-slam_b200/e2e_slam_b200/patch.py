@@ -1,0 +1,132 @@
+"""Drop-in wiring for the reference's driver scripts (train_depth.py, online_adaption.py, ...).
+
+Tier (i) -- unmodified scripts, one line added before their imports:
+
+    import e2e_slam_b200.patch as e2e_patch; e2e_patch.install()
+
+`install()` pre-seeds `sys.modules` so that the scripts' own import statements
+    from loss.losses import *                                   (train_depth.py:22)
+    from depth_estimation.view_synthesis import BackprojectDepth, Project3D          (:30)
+    from slam.custom_slam import image_recover_slam              (:27)
+    from gradslam.slam import PointFusion, ICPSLAM ; from gradslam import Pointclouds, RGBDImages   (:33-38)
+    from gradslam.geometry.geometryutils import transform_pointcloud                 (online_adaption.py:36)
+    from chamferdist import ChamferDistance ; from chamferdist.chamfer import knn_points (loss/losses.py:3)
+resolve to this package.  `depth_estimation.networks`, `utils.*` and the dataset classes stay the
+reference's / gradslam's own (they are host code outside the hot path).
+
+Tier (ii) -- the fused op behind the scripts' method names:
+
+    e2e_patch.fuse(Depth_Estimation)        # or SLAM from online_adaption.py
+
+replaces `novel_view_synthesis` and `compute_photometric_loss` (train_depth.py:545-613, 707-727) by versions
+that run ONE fused forward kernel per source frame and hand autograd ONE fused backward kernel, while still
+filling `outputs[("synthesized_frame", f)]` / `outputs[("valid_mask", f)]` that the scripts' plotting reads.
+"""
+import sys
+import types
+
+import torch
+
+from . import losses, ops, slam, view_synthesis
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__e2e_slam_b200__ = True
+    return m
+
+
+def install(grid_sample=False, keep_real_gradslam_datasets=True):
+    """Route the reference's imports to e2e_slam_b200.  Idempotent.  With grid_sample=True,
+    torch.nn.functional.grid_sample is also replaced for CUDA fp32 bilinear zeros|border calls."""
+    sm = sys.modules
+    # --- the reference's own modules on the hot path -----------------------------------------------
+    public = {k: v for k, v in vars(losses).items() if not k.startswith("_")}
+    sm["loss.losses"] = _module("loss.losses", **public, __all__=[k for k in public if k not in ("torch", "nn", "ops", "namedtuple")])
+    sm["depth_estimation.view_synthesis"] = view_synthesis
+    sm["slam.custom_slam"] = _module("slam.custom_slam", image_recover_slam=slam.image_recover_slam, Pointclouds=slam.Pointclouds)
+    # --- gradslam -------------------------------------------------------------------------------------
+    real_datasets = None
+    if keep_real_gradslam_datasets and "gradslam" not in sm:
+        try:
+            import importlib
+            real_datasets = importlib.import_module("gradslam.datasets")
+        except Exception:
+            real_datasets = None
+        for k in [k for k in sm if k == "gradslam" or k.startswith("gradslam.")]:
+            if k != "gradslam.datasets" and not k.startswith("gradslam.datasets."):
+                del sm[k]
+
+    def _no_dataset(*a, **k):
+        raise ImportError("gradslam.datasets (ICL/TUM loaders) is dataset IO outside the hot path; install gradslam "
+                          "to use it, or feed tensors of the same layout (see e2e_slam_b200.synthetic)")
+
+    fusionutils = _module("gradslam.slam.fusionutils", find_active_map_points=_find_active_map_points)
+    gs_slam = _module("gradslam.slam", PointFusion=slam.PointFusion, ICPSLAM=slam.ICPSLAM, fusionutils=fusionutils)
+    geomutils = _module("gradslam.geometry.geometryutils", transform_pointcloud=slam.transform_pointcloud)
+    geometry = _module("gradslam.geometry", geometryutils=geomutils)
+    structures = _module("gradslam.structures", Pointclouds=slam.Pointclouds, RGBDImages=slam.RGBDImages)
+    datasets = real_datasets or _module("gradslam.datasets", ICL=_no_dataset, TUM=_no_dataset)
+    gs = _module("gradslam", Pointclouds=slam.Pointclouds, RGBDImages=slam.RGBDImages, slam=gs_slam, geometry=geometry,
+                 structures=structures, datasets=datasets)
+    gs.__path__ = []
+    sm.update({"gradslam": gs, "gradslam.slam": gs_slam, "gradslam.slam.fusionutils": fusionutils, "gradslam.geometry": geometry,
+               "gradslam.geometry.geometryutils": geomutils, "gradslam.structures": structures, "gradslam.datasets": datasets})
+    # --- chamferdist ----------------------------------------------------------------------------------
+    chamfer = _module("chamferdist.chamfer", knn_points=losses.knn_points)
+    cd = _module("chamferdist", ChamferDistance=losses.ChamferDistance, chamfer=chamfer)
+    cd.__path__ = []
+    sm.update({"chamferdist": cd, "chamferdist.chamfer": chamfer})
+    if grid_sample:
+        _patch_grid_sample()
+
+
+def _find_active_map_points(pointclouds, rgbdimages):
+    raise NotImplementedError("find_active_map_points is imported by online_adaption.py:35 but never called; the active-point "
+                              "test runs inside PointFusion.step's association kernel (e2e_fusion_associate)")
+
+
+_torch_grid_sample = torch.nn.functional.grid_sample
+
+
+def _patch_grid_sample():
+    def grid_sample(input, grid, mode="bilinear", padding_mode="zeros", align_corners=None):
+        if (input.is_cuda and input.dtype == torch.float32 and input.dim() == 4 and mode == "bilinear"
+                and padding_mode in ("zeros", "border")):
+            return view_synthesis.grid_sample(input, grid, mode, padding_mode, bool(align_corners))
+        return _torch_grid_sample(input, grid, mode=mode, padding_mode=padding_mode, align_corners=align_corners)
+    torch.nn.functional.grid_sample = grid_sample
+
+
+# ---- tier (ii): fused replacements for the scripts' methods ------------------------------------------
+def fused_novel_view_synthesis(self, inputs):
+    """Replacement for Depth_Estimation.novel_view_synthesis / SLAM.novel_view_synthesis (non-geometric
+    branch, train_depth.py:578-590): one fused kernel per source frame."""
+    if self.args.LOSS.geometric:
+        raise NotImplementedError("the fused op covers the photometric branch; LOSS.geometric uses the granular ops")
+    outputs = {}
+    for frame in self.args.DATA.frames[1:]:
+        T = inputs["T", frame]
+        if T.dim() == 4:
+            T = T.squeeze(1)                      # online_adaption.py:446
+        loss_map, syn, valid, _ = ops.warp_photometric(
+            inputs["target_depth"], inputs["Inverse_K"], inputs["K"], T, inputs["source_frame", frame], inputs["target_frame"],
+            padding_mode=self.args.MODEL.padding_mode, photometric_mask=bool(self.args.LOSS.photometric_mask), need_outputs=True)
+        outputs[("valid_mask", frame)] = valid
+        outputs[("synthesized_frame", frame)] = syn
+        outputs[("photometric_map", frame)] = loss_map
+    return outputs
+
+
+def fused_compute_photometric_loss(self, inputs, outputs):
+    """Replacement for compute_photometric_loss (train_depth.py:707-727): the per-frame maps were produced by
+    the fused forward already; concatenate them exactly as the reference does (:726)."""
+    return torch.cat([outputs[("photometric_map", frame)] for frame in self.args.DATA.frames[1:]], 1)
+
+
+def fuse(cls):
+    """Swap a reference driver class's view-synthesis + photometric-loss methods for the fused op."""
+    cls.novel_view_synthesis = fused_novel_view_synthesis
+    cls.compute_photometric_loss = fused_compute_photometric_loss
+    return cls

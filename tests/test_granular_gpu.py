@@ -160,3 +160,30 @@ def test_smoothness_full_size():
         a, r = dg.grad.cpu().numpy(), do.grad.numpy()
         err = np.abs(a - r)[~kink].max() / np.abs(r).max()
         assert err <= RTOL, err
+
+
+def test_fused_driver_methods_on_goldens(golden):
+    """patch.fuse(): the scripts' novel_view_synthesis + compute_photometric_loss replaced by the fused op, then
+    the reference's own reduction (train_depth.py:629, 657).  Same numbers as the reference, bit for bit."""
+    from types import SimpleNamespace as NS
+    from e2e_slam_b200 import patch
+    g = golden
+
+    class Driver:                      # stands in for Depth_Estimation / SLAM: only `args` is read
+        args = NS(DATA=NS(frames=[0, -1]), MODEL=NS(padding_mode=str(g["padding_mode"])),
+                  LOSS=NS(geometric=False, photometric_mask=bool(g["use_mask"])))
+    patch.fuse(Driver)
+    colors = _d(g, "colors")
+    depth = _d(g, "depth").requires_grad_(True)
+    inputs = {"target_depth": depth, "Inverse_K": _d(g, "inv_K"), "K": _d(g, "K"), ("T", -1): _d(g, "T"),
+              ("source_frame", -1): colors[:, 0].permute(0, 3, 1, 2), "target_frame": colors[:, 1].permute(0, 3, 1, 2)}
+    drv = Driver()
+    outputs = drv.novel_view_synthesis(inputs)
+    photometric = drv.compute_photometric_loss(inputs, outputs).mean(1, keepdim=True)
+    loss = photometric.mean()
+    loss.backward()
+    assert same_values(outputs[("synthesized_frame", -1)].cpu().numpy(), g["syn"]) == 0
+    assert same_values(outputs[("valid_mask", -1)].cpu().numpy(), g["valid"]) == 0
+    assert same_values(photometric.detach().cpu().numpy(), g["loss_map"]) == 0
+    assert abs(float(loss.detach()) - float(g["loss"])) <= RTOL * float(g["loss"])
+    assert_grad_close("g_depth", depth.grad.cpu().numpy(), g["g_depth"], g["g_depth_f64"])
