@@ -105,7 +105,8 @@ __device__ __forceinline__ PixConst pix_const(const WPParams &p)
     return PixConst{p.eps, p.wm1, p.hm1, p.half_w, p.half_h, p.rcpW, p.rcpH, p.border, p.div_exact};
 }
 
-__device__ __forceinline__ void project_pixel(const float *cam, const PixConst &k, int x, int y, float d, Proj &o)
+// Pixel -> camera point -> projected homogeneous coordinate (everything before the divisions).
+__device__ __forceinline__ void project_point(const float *cam, float eps, int x, int y, float d, Proj &o)
 {
     const float fx = (float)x, fy = (float)y;
     // sgemm k-loop (k = 0,1,2) then * depth               view_synthesis.py:36-38
@@ -119,7 +120,12 @@ __device__ __forceinline__ void project_pixel(const float *cam, const PixConst &
     o.c0 = xadd(xfma(P[2], o.X2, xfma(P[1], o.X1, xmul(P[0], o.X0))), P[3]);
     o.c1 = xadd(xfma(P[6], o.X2, xfma(P[5], o.X1, xmul(P[4], o.X0))), P[7]);
     o.c2 = xadd(xfma(P[10], o.X2, xfma(P[9], o.X1, xmul(P[8], o.X0))), P[11]);
-    o.z = xadd(o.c2, k.eps);                               // :60
+    o.z = xadd(o.c2, eps);                                 // :60
+}
+
+__device__ __forceinline__ void project_pixel(const float *cam, const PixConst &k, int x, int y, float d, Proj &o)
+{
+    project_point(cam, k.eps, x, y, d, o);
     const float u = xdiv(o.c0, o.z), v = xdiv(o.c1, o.z);
     o.gx = xmul(xsub(div_coord(u, k.wm1, k.rcpW, k.exact), 0.5f), 2.0f);   // :66-68
     o.gy = xmul(xsub(div_coord(v, k.hm1, k.rcpH, k.exact), 0.5f), 2.0f);

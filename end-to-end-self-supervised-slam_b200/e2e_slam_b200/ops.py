@@ -119,6 +119,79 @@ class _WarpPhotometric(torch.autograd.Function):
                 None, None, None, None, None)
 
 
+class _WarpPhotometricMean(torch.autograd.Function):
+    """Scalar mean photometric loss through the single-pass value+gradient kernel (e2e_warp_photo_vg):
+    forward() produces the loss and, in the same sweep, its gradients for an upstream gradient of 1;
+    backward() only rescales them by the actual upstream scalar (a kernel that exits immediately when that
+    scalar is 1, which is the reference's `loss.backward()`)."""
+
+    @staticmethod
+    def forward(ctx, depth, inv_K, K, T, src, tgt, padding_mode, use_mask, eps):
+        f32(depth, "depth"), f32(src, "source frame"), f32(tgt, "target frame")
+        if depth.dim() != 4 or depth.shape[1] != 1:
+            raise ValueError(f"depth must be (B,1,H,W), got {tuple(depth.shape)}")
+        B, _, H, W = depth.shape
+        if tuple(src.shape) != (B, 3, H, W) or tuple(tgt.shape) != (B, 3, H, W):
+            raise ValueError(f"source/target frames must be ({B},3,{H},{W}), got {tuple(src.shape)} / {tuple(tgt.shape)}")
+        depth_c = depth.contiguous()
+        inv_K_c, K_c, T_c = _mat44(inv_K, B, "inv_K"), _mat44(K, B, "K"), _mat44(T, B, "T")
+        prepare_divisors(W - 1, H - 1, 9.0, 3.0)
+        dev = depth.device
+        pad = _pad_code(padding_mode)
+        need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
+        if not (need_depth or need_K or need_T or need_src):       # value only: the lean forward kernel
+            ws, ws_bytes = _workspace(B, H, W, dev)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib().e2e_warp_photo_fwd(ptr(depth_c), ptr(inv_K_c), ptr(K_c), ptr(T_c), ptr(src), strides4(src),
+                                              ptr(tgt), strides4(tgt), B, H, W, pad, int(bool(use_mask)),
+                                              ctypes.c_float(eps), None, None, None, None, ptr(loss), ptr(ws), ws_bytes,
+                                              stream_ptr())
+            check(rc, "e2e_warp_photo_fwd")
+            return loss.reshape(())
+        n = lib().e2e_warp_photo_vg_workspace_bytes(B, H, W)
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad_depth = torch.empty_like(depth_c)
+        grad_src = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
+        grad_P = torch.empty(B, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
+        with torch.cuda.device(dev):
+            rc = lib().e2e_warp_photo_vg(ptr(depth_c), ptr(inv_K_c), ptr(K_c), ptr(T_c), ptr(src), strides4(src),
+                                         ptr(tgt), strides4(tgt), B, H, W, pad, int(bool(use_mask)), ctypes.c_float(eps),
+                                         ptr(loss), ptr(grad_depth), ptr(grad_src),
+                                         strides4(grad_src) if grad_src is not None else None,
+                                         ptr(grad_P), ptr(ws), n, stream_ptr())
+        check(rc, "e2e_warp_photo_vg")
+        ctx.grads = (grad_depth, grad_src, grad_P)
+        ctx.save_for_backward(K_c, T_c)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grads is None:
+            raise RuntimeError("warp_photometric_loss evaluates its gradients in the forward sweep and hands them out "
+                               "once; for a second backward pass (retain_graph) use warp_photometric(...).mean()")
+        grad_depth, grad_src, grad_P = ctx.grads
+        ctx.grads = None
+        K, T = ctx.saved_tensors
+        need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
+        g = f32(g, "grad").reshape(1).contiguous()
+        with torch.cuda.device(grad_depth.device):
+            rc = lib().e2e_scale_by_scalar(ptr(grad_depth), grad_depth.numel(),
+                                           ptr(grad_src), grad_src.numel() if grad_src is not None else 0,
+                                           ptr(grad_P), grad_P.numel() if grad_P is not None else 0,
+                                           ptr(g), stream_ptr())
+        check(rc, "e2e_scale_by_scalar")
+        grad_K = grad_T = None
+        if grad_P is not None:
+            if need_T:
+                grad_T = torch.matmul(K[:, :3, :].transpose(1, 2), grad_P)
+            if need_K:
+                grad_K = torch.zeros_like(K)
+                grad_K[:, :3, :] = torch.matmul(grad_P, T.transpose(1, 2))
+        return (grad_depth if need_depth else None, None, grad_K, grad_T, grad_src, None, None, None, None)
+
+
 def warp_photometric(depth, inv_K, K, T, source_frame, target_frame, padding_mode="border",
                      photometric_mask=True, need_outputs=False, eps=1e-7):
     """Per-pixel photometric loss of warping `source_frame` into the target view.
@@ -134,8 +207,8 @@ def warp_photometric_loss(depth, inv_K, K, T, source_frame, target_frame, paddin
                           photometric_mask=True, eps=1e-7):
     """Scalar `photometric_loss(...).mean()` for one source frame (train_depth.py:657), lean path:
     neither the synthesized frame nor the loss map is written to memory."""
-    return _WarpPhotometric.apply(depth, inv_K, K, T, source_frame, target_frame, padding_mode,
-                                  photometric_mask, eps, "mean", False)
+    return _WarpPhotometricMean.apply(depth, inv_K, K, T, source_frame, target_frame, padding_mode,
+                                      photometric_mask, eps)
 
 
 class _SSIM(torch.autograd.Function):
@@ -208,12 +281,28 @@ class WarpPhotoPlan:
         with torch.cuda.device(self.device):
             prepare_divisors(W - 1, H - 1, 9.0, 3.0)
         self.ws, self.ws_bytes = _workspace(B, H, W, self.device)
+        self.vg_ws_bytes = lib().e2e_warp_photo_vg_workspace_bytes(B, H, W)
+        self.vg_ws = torch.empty(self.vg_ws_bytes, dtype=torch.uint8, device=self.device)
         f = dict(dtype=torch.float32, device=self.device)
         self.loss = torch.empty(1, **f)
         self.grad_depth = torch.empty(B, 1, H, W, **f)
         self.grad_src = torch.empty(B, 3, H, W, **f) if need_src_grad else None
         self.grad_P = torch.empty(B, 3, 4, **f) if need_pose_grad else None
         self._gs_strides = strides4(self.grad_src) if need_src_grad else None
+
+    def value_and_grad(self, depth, inv_K, K, T, src, tgt):
+        """loss (device scalar) and d loss / d {depth, src, (K@T)[:3]} in ONE sweep (e2e_warp_photo_vg):
+        zero-fill of grad_src + fused kernel + two tiny fixed-order reductions."""
+        if self.grad_src is not None:
+            self.grad_src.zero_()          # the kernel accumulates into it with red.global.add
+        with torch.cuda.device(self.device):
+            rc = lib().e2e_warp_photo_vg(ptr(depth), ptr(inv_K), ptr(K), ptr(T), ptr(src), strides4(src),
+                                         ptr(tgt), strides4(tgt), self.B, self.H, self.W, self.pad, self.mask,
+                                         ctypes.c_float(self.eps), ptr(self.loss), ptr(self.grad_depth),
+                                         ptr(self.grad_src), self._gs_strides, ptr(self.grad_P),
+                                         ptr(self.vg_ws), self.vg_ws_bytes, stream_ptr())
+        check(rc, "e2e_warp_photo_vg")
+        return self.loss, self.grad_depth, self.grad_src, self.grad_P
 
     def forward(self, depth, inv_K, K, T, src, tgt):
         with torch.cuda.device(self.device):

@@ -78,6 +78,25 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
                        float *grad_depth, float *grad_src, const int64_t grad_src_strides[4], float *grad_P,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* Single-pass value + gradient of the SCALAR loss  mean_{B,H,W} photometric_loss(...)  (the reference's use:
+ * `losses += photometric.mean()` train_depth.py:657 followed by `loss.backward()` :307): one sweep over the
+ * inputs produces loss_mean [1] and d loss_mean / d {depth, source image, P = (K@T)[:3]} for an upstream
+ * gradient of 1.  Same argument meaning as e2e_warp_photo_fwd / _bwd: grad_depth [B,1,H,W] written,
+ * grad_src ACCUMULATED into a caller-zeroed buffer (NULL to skip), grad_P [B,3,4] written (NULL to skip).
+ * Workspace: e2e_warp_photo_vg_workspace_bytes().  e2e_scale_by_scalar multiplies up to three gradient
+ * buffers in place by a device-resident upstream scalar and exits without touching memory when it is 1. */
+size_t e2e_warp_photo_vg_workspace_bytes(int B, int H, int W);
+
+int e2e_warp_photo_vg(const float *depth, const float *inv_K, const float *K, const float *T,
+                      const float *src, const int64_t src_strides[4],
+                      const float *tgt, const int64_t tgt_strides[4],
+                      int B, int H, int W, int padding_mode, int use_mask, float eps,
+                      float *loss_mean, float *grad_depth, float *grad_src, const int64_t grad_src_strides[4],
+                      float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
+
+int e2e_scale_by_scalar(float *a, long long na, float *b, long long nb, float *c, long long nc,
+                        const float *scalar, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stand-alone SSIM / photometric loss on given images (tier (i) drop-in for loss/losses.py:6-37 and
  * :97-117, also used for the auto-masking variant train_depth.py:729-750).  x, y are [B,C,H,W] via
