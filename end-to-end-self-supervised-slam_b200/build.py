@@ -40,7 +40,8 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE] + sources() + ["-o", LIB]
+    extra = os.environ.get("E2E_NVCC_FLAGS", "").split()      # kernel-tuning experiments only
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", INCLUDE] + sources() + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -12,8 +12,12 @@ dev = torch.device("cuda:0")
 d = make_pairs(P, H, W, "icl", seed=0, device=dev)
 src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)
 plan = ops.WarpPhotoPlan(P, H, W, dev)
+mode = sys.argv[3] if len(sys.argv) > 3 else "vg"
 for _ in range(iters):
-    plan.forward(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
-    plan.backward(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+    if mode == "vg":
+        plan.value_and_grad(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+    else:
+        plan.forward(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+        plan.backward(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
 torch.cuda.synchronize()
 print("ok", float(plan.loss))

@@ -36,9 +36,10 @@ t_b = timeit(lambda: plan.backward(*a), iters)
 gd_b, gs_b, gp_b = plan.grad_depth.clone(), plan.grad_src.clone(), plan.grad_P.clone()
 t_v = timeit(lambda: plan.value_and_grad(*a), iters)
 lv = float(plan.loss)
+gd_v, gs_v, gp_v = plan.grad_depth.clone(), plan.grad_src.clone(), plan.grad_P.clone()
 t_z = timeit(lambda: plan.grad_src.zero_(), iters)
 npx = P * H * W
 rel = lambda x, y: float((x - y).abs().max() / y.abs().max())
 print(f"pairs={P} fwd {t_f:.3f} ms  bwd(+zero) {t_b:.3f} ms  vg(+zero) {t_v:.3f} ms  zero {t_z:.3f} ms")
 print(f"vg: {npx / t_v / 1e6:.2f} Gpx/s, {72 * npx / t_v / 1e6:.0f} GB/s algorithmic (72 B/px)")
-print(f"loss fwd {lf:.8f} vg {lv:.8f}  rel diffs vs bwd kernel: depth {rel(plan.grad_depth, gd_b):.2e} src {rel(plan.grad_src, gs_b):.2e} P {rel(plan.grad_P, gp_b):.2e}")
+print(f"loss fwd {lf:.8f} vg {lv:.8f}  rel diffs vs bwd kernel: depth {rel(gd_v, gd_b):.2e} src {rel(gs_v, gs_b):.2e} P {rel(gp_v, gp_b):.2e}")
