@@ -35,16 +35,6 @@ def _mat44(m, B, name):
     return m.contiguous()
 
 
-def _zeros_like_image(src):
-    """Zero gradient buffer for a (B,3,H,W) image with the image's own memory format: channels-last views
-    (train_depth.py:451-453) get a channels-last buffer, so the kernels' interleaved-RGB path (adjacent
-    words per tap, two base addresses per pixel) serves the scatter as well as the gather."""
-    B, C, H, W = src.shape
-    if src.stride(1) == 1 and src.stride(3) == C:
-        return torch.zeros(B, H, W, C, dtype=torch.float32, device=src.device).permute(0, 3, 1, 2)
-    return torch.zeros(B, C, H, W, dtype=torch.float32, device=src.device)
-
-
 def _workspace(B, H, W, device):
     n = lib().e2e_warp_photo_workspace_bytes(B, H, W)
     return torch.empty(n, dtype=torch.uint8, device=device), n
@@ -101,7 +91,7 @@ class _WarpPhotometric(torch.autograd.Function):
         dev = depth.device
         need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
         grad_depth = torch.empty_like(depth)
-        grad_src = _zeros_like_image(src) if need_src else None
+        grad_src = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
         grad_P = torch.empty(B, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
         ws, ws_bytes = _workspace(B, H, W, dev)
         if mode == "map":
@@ -163,7 +153,7 @@ class _WarpPhotometricMean(torch.autograd.Function):
         ws = torch.empty(n, dtype=torch.uint8, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         grad_depth = torch.empty_like(depth_c)
-        grad_src = _zeros_like_image(src) if need_src else None
+        grad_src = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
         grad_P = torch.empty(B, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
         with torch.cuda.device(dev):
             rc = lib().e2e_warp_photo_vg(ptr(depth_c), ptr(inv_K_c), ptr(K_c), ptr(T_c), ptr(src), strides4(src),
@@ -284,7 +274,7 @@ class WarpPhotoPlan:
     """
 
     def __init__(self, B, H, W, device, padding_mode="border", photometric_mask=True, eps=1e-7,
-                 need_src_grad=True, need_pose_grad=True, channels_last=True):
+                 need_src_grad=True, need_pose_grad=True):
         self.B, self.H, self.W = B, H, W
         self.device = torch.device(device)
         self.pad, self.mask, self.eps = _pad_code(padding_mode), int(bool(photometric_mask)), float(eps)
@@ -296,9 +286,8 @@ class WarpPhotoPlan:
         f = dict(dtype=torch.float32, device=self.device)
         self.loss = torch.empty(1, **f)
         self.grad_depth = torch.empty(B, 1, H, W, **f)
-        self.grad_src = None
-        if need_src_grad:       # same memory format as the source frames (channels-last views in the reference)
-            self.grad_src = torch.empty(B, H, W, 3, **f).permute(0, 3, 1, 2) if channels_last else torch.empty(B, 3, H, W, **f)
+        # planar: the kernel's atomics of a warp then fall into 4 sectors per instruction instead of 12
+        self.grad_src = torch.empty(B, 3, H, W, **f) if need_src_grad else None
         self.grad_P = torch.empty(B, 3, 4, **f) if need_pose_grad else None
         self._gs_strides = strides4(self.grad_src) if need_src_grad else None
 
