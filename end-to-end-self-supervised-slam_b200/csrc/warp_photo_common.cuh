@@ -268,7 +268,7 @@ __device__ __forceinline__ void window_sums(const float *wx, const float *wy, fl
 }
 
 struct SsimVals {
-    float mux, muy, A1, A2, B1, B2, n, dn, Q, sraw, s;
+    float mux, muy, A1, A2, B1, B2, n, dn, Q, sraw, s, rdn;
 };
 
 template <bool IEEE>
