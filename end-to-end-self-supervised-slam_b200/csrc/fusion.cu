@@ -14,7 +14,7 @@
 namespace e2e {
 
 constexpr int FU_NT = 256;
-constexpr int SCAN_CHUNK = 1024;       // pixels per CTA in the append scan (row-major chunks)
+constexpr int SCAN_CHUNK = 256;        // pixels per CTA in the append scan (row-major chunks): one pixel per thread
 
 struct Cam {
     float ifx, ify, icx, icy;          // closed-form inverse intrinsics
@@ -159,42 +159,70 @@ struct AssocParams {
     int H, W;
     float dist_th, dot_th, u_hi, v_hi;
     unsigned long long *keys, *index_map;
+    int *cand;
 };
 
-template <int PASS>
-__global__ void __launch_bounds__(FU_NT) associate_kernel(const AssocParams p)
+// Pass 1: every map point is projected into the live frame; candidates (in the frustum, close in space, similar
+// normal) race for their pixel with a 64-bit atomicMin of the key (1/(c+1e-20), dist^2) and remember their pixel in
+// cand[n] (-1 = not a candidate).  All per-point loads (point, normal, confidence) are issued up front, so the
+// dependent chain is two memory round trips (point data -> live-frame gather) instead of four.
+__global__ void __launch_bounds__(FU_NT) associate_pass1_kernel(const AssocParams p)
 {
     __shared__ Cam c;
     stage_cam(p.K, p.pose, &c);
     const long long N = *p.n_map;
     for (long long n = (long long)blockIdx.x * FU_NT + threadIdx.x; n < N; n += (long long)gridDim.x * FU_NT) {
         const float px = p.pts[n * 3], py = p.pts[n * 3 + 1], pz = p.pts[n * 3 + 2];
+        const float nx = p.nrm[n * 3], ny = p.nrm[n * 3 + 1], nz = p.nrm[n * 3 + 2];
+        const float cc = p.cc[n];
+        int cand = -1;
         // 1. active map points: into the live camera, in front, inside the frustum, round to a pixel
         const float qx = xadd(dot3_lr(c.Ri[0], c.Ri[1], c.Ri[2], px, py, pz), c.ti[0]);
         const float qy = xadd(dot3_lr(c.Ri[3], c.Ri[4], c.Ri[5], px, py, pz), c.ti[1]);
         const float qz = xadd(dot3_lr(c.Ri[6], c.Ri[7], c.Ri[8], px, py, pz), c.ti[2]);
-        if (!(qz > 0.0f)) continue;
-        const float h0 = xadd(dot3_lr(c.K[0], c.K[1], c.K[2], qx, qy, qz), c.K[3]);
-        const float h1 = xadd(dot3_lr(c.K[4], c.K[5], c.K[6], qx, qy, qz), c.K[7]);
-        const float h2 = xadd(dot3_lr(c.K[8], c.K[9], c.K[10], qx, qy, qz), c.K[11]);
-        const float u = xdiv(h0, h2), v = xdiv(h1, h2);
-        if (!(u > -1e-3f && u < p.u_hi && v > -1e-3f && v < p.v_hi)) continue;
-        int w = __float2int_rn(u), h = __float2int_rn(v);       // round half to even, like torch.round
-        w = min(max(w, 0), p.W - 1);
-        h = min(max(h, 0), p.H - 1);
-        const int pix = h * p.W + w;
-        // 2. similar: close in space, similar normal
+        if (qz > 0.0f) {
+            const float h0 = xadd(dot3_lr(c.K[0], c.K[1], c.K[2], qx, qy, qz), c.K[3]);
+            const float h1 = xadd(dot3_lr(c.K[4], c.K[5], c.K[6], qx, qy, qz), c.K[7]);
+            const float h2 = xadd(dot3_lr(c.K[8], c.K[9], c.K[10], qx, qy, qz), c.K[11]);
+            const float u = xdiv(h0, h2), v = xdiv(h1, h2);
+            if (u > -1e-3f && u < p.u_hi && v > -1e-3f && v < p.v_hi) {
+                int w = __float2int_rn(u), h = __float2int_rn(v);       // round half to even, like torch.round
+                w = min(max(w, 0), p.W - 1);
+                h = min(max(h, 0), p.H - 1);
+                const int pix = h * p.W + w;
+                // 2. similar: close in space, similar normal (both live-frame gathers issued together)
+                const float vx = p.vertex_g[pix * 3], vy = p.vertex_g[pix * 3 + 1], vz = p.vertex_g[pix * 3 + 2];
+                const float gx = p.normal_g[pix * 3], gy = p.normal_g[pix * 3 + 1], gz = p.normal_g[pix * 3 + 2];
+                const float dx = xsub(vx, px), dy = xsub(vy, py), dz = xsub(vz, pz);
+                const float dist2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+                const float dot = dot3_lr(gx, gy, gz, nx, ny, nz);
+                if (__fsqrt_rn(dist2) < p.dist_th && dot > p.dot_th) {
+                    // 3. best unique: lexicographic minimum of (1/(c + 1e-20), dist^2, n) per pixel
+                    const float inv_c = xdiv(1.0f, xadd(cc, 1e-20f));
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(inv_c) << 32) | (unsigned long long)__float_as_uint(dist2);
+                    atomicMin(p.keys + pix, key);
+                    cand = pix;
+                }
+            }
+        }
+        p.cand[n] = cand;
+    }
+}
+
+// Pass 2: among the candidates whose key won their pixel, the smallest map index wins (ties on the full key).
+// Non-candidates leave after one 4-byte load; candidates recompute their key with the same operations.
+__global__ void __launch_bounds__(FU_NT) associate_pass2_kernel(const AssocParams p)
+{
+    const long long N = *p.n_map;
+    for (long long n = (long long)blockIdx.x * FU_NT + threadIdx.x; n < N; n += (long long)gridDim.x * FU_NT) {
+        const int pix = p.cand[n];
+        if (pix < 0) continue;
+        const float px = p.pts[n * 3], py = p.pts[n * 3 + 1], pz = p.pts[n * 3 + 2];
         const float dx = xsub(p.vertex_g[pix * 3], px), dy = xsub(p.vertex_g[pix * 3 + 1], py), dz = xsub(p.vertex_g[pix * 3 + 2], pz);
         const float dist2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-        if (!(__fsqrt_rn(dist2) < p.dist_th)) continue;
-        const float dot = dot3_lr(p.normal_g[pix * 3], p.normal_g[pix * 3 + 1], p.normal_g[pix * 3 + 2],
-                                  p.nrm[n * 3], p.nrm[n * 3 + 1], p.nrm[n * 3 + 2]);
-        if (!(dot > p.dot_th)) continue;
-        // 3. best unique: lexicographic minimum of (1/(c + 1e-20), dist^2, n) per pixel
         const float inv_c = xdiv(1.0f, xadd(p.cc[n], 1e-20f));
         const unsigned long long key = ((unsigned long long)__float_as_uint(inv_c) << 32) | (unsigned long long)__float_as_uint(dist2);
-        if (PASS == 1) atomicMin(p.keys + pix, key);
-        else if (p.keys[pix] == key) atomicMin(p.index_map + pix, (unsigned long long)n);
+        if (p.keys[pix] == key) atomicMin(p.index_map + pix, (unsigned long long)n);
     }
 }
 
@@ -430,11 +458,13 @@ int e2e_fusion_associate(const float *map_points, const float *map_normals, cons
                          const long long *n_map, long long n_upper,
                          const float *K, const float *pose, const float *vertex_g, const float *normal_g,
                          int H, int W, float dist_th, float dot_th,
-                         unsigned long long *keys, long long *index_map, void *stream)
+                         unsigned long long *keys, int *candidates, long long *index_map, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     E2E_REQUIRE(n_map && K && pose && vertex_g && normal_g && keys && index_map && H > 0 && W > 0 && n_upper >= 0,
                 "fusion_associate: bad arguments");
+    E2E_REQUIRE(n_upper == 0 || candidates, "fusion_associate: candidates scratch (int32[n_upper]) is null");
+    E2E_REQUIRE((long long)H * W < (1ll << 31), "fusion_associate: image too large");
     E2E_REQUIRE(n_upper == 0 || (map_points && map_normals && map_ccount), "fusion_associate: null map");
     // keys = all ones (maximum); index_map = all ones = -1 as int64 = maximum as uint64
     cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * (size_t)H * W, st);
@@ -445,10 +475,10 @@ int e2e_fusion_associate(const float *map_points, const float *map_normals, cons
     p.K = K; p.pose = pose; p.vertex_g = vertex_g; p.normal_g = normal_g; p.H = H; p.W = W;
     p.dist_th = dist_th; p.dot_th = dot_th;
     p.u_hi = (float)((double)W - 0.999); p.v_hi = (float)((double)H - 0.999);
-    p.keys = keys; p.index_map = (unsigned long long *)index_map;
+    p.keys = keys; p.index_map = (unsigned long long *)index_map; p.cand = candidates;
     const int grid = grid_for(n_upper);
-    associate_kernel<1><<<grid, FU_NT, 0, st>>>(p);
-    associate_kernel<2><<<grid, FU_NT, 0, st>>>(p);
+    associate_pass1_kernel<<<grid, FU_NT, 0, st>>>(p);
+    associate_pass2_kernel<<<grid, FU_NT, 0, st>>>(p);
     count_launch(2);
     return finish_launch("fusion_associate");
 }
@@ -502,4 +532,57 @@ int e2e_fusion_merge_append_bwd(const float *grad_points, const float *grad_colo
     return finish_launch("fusion_merge_append_bwd");
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Whole-sequence fusion with known poses (slam/custom_slam.py:26-34 / PointFusion.forward with odom="gt", no
+ * autograd): the frame loop runs here, so the host pays one call per SEQUENCE instead of ~15 launches, memsets and
+ * allocations per frame from Python (which bound the per-frame time at ~130 us on the host, more than the kernels).
+ * --------------------------------------------------------------------------------------------- */
+static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
+
+size_t e2e_fusion_sequence_workspace_bytes(int H, int W, long long capacity)
+{
+    const size_t hw = (size_t)H * W;
+    return align256(hw * 12) * 2 + align256(hw * 4) + align256(hw) + align256(hw * 8) * 2 + align256((size_t)capacity * 4) +
+           align256(e2e_fusion_workspace_bytes(H, W)) + 256;
+}
+
+int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, const float *poses, int L, int H, int W,
+                        float sigma, float dist_th, float dot_th,
+                        float *map_points, float *map_normals, float *map_colors, float *map_ccount,
+                        long long *n_map, long long n_upper, long long capacity,
+                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    E2E_REQUIRE(depth && rgb && K && poses && map_points && map_normals && map_colors && map_ccount && n_map && workspace,
+                "fusion_sequence: null argument");
+    E2E_REQUIRE(L >= 0 && H > 0 && W > 0 && n_upper >= 0, "fusion_sequence: bad sizes");
+    E2E_REQUIRE(capacity >= n_upper + (long long)L * H * W, "fusion_sequence: capacity must be >= n_upper + L*H*W");
+    E2E_REQUIRE(workspace_bytes >= e2e_fusion_sequence_workspace_bytes(H, W, capacity), "fusion_sequence: workspace too small");
+    const size_t hw = (size_t)H * W;
+    unsigned char *w = (unsigned char *)workspace;
+    float *vg = (float *)w;                                 w += align256(hw * 12);
+    float *ng = (float *)w;                                 w += align256(hw * 12);
+    float *alpha = (float *)w;                              w += align256(hw * 4);
+    unsigned char *valid = w;                               w += align256(hw);
+    unsigned long long *keys = (unsigned long long *)w;     w += align256(hw * 8);
+    long long *index_map = (long long *)w;                  w += align256(hw * 8);
+    int *cand = (int *)w;                                   w += align256((size_t)capacity * 4);
+    void *ws = w;
+    const size_t ws_bytes = e2e_fusion_workspace_bytes(H, W);
+    for (int s = 0; s < L; s++) {
+        const float *pose = poses + (size_t)s * 16;
+        if (int rc = e2e_rgbd_maps(depth + (size_t)s * hw, nullptr, K, pose, H, W, sigma, vg, ng, alpha, valid, stream)) return rc;
+        const long long upper = n_upper + (long long)s * H * W;
+        if (int rc = e2e_fusion_associate(map_points, map_normals, map_ccount, n_map, upper, K, pose, vg, ng, H, W, dist_th, dot_th,
+                                          keys, cand, index_map, stream)) return rc;
+        // the new point count goes to the scratch slot n_map[1] (fuse_append still needs the old count), then replaces n_map[0]
+        if (int rc = e2e_fusion_merge_append(map_points, map_normals, map_colors, map_ccount, n_map, capacity, vg, ng,
+                                             rgb + (size_t)s * hw * 3, alpha, valid, index_map, H, W, nullptr, n_map + 1,
+                                             ws, ws_bytes, stream)) return rc;
+        if (cudaMemcpyAsync(n_map, n_map + 1, sizeof(long long), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess)
+            return finish_launch("fusion_sequence: n_map update");
+    }
+    return 0;
+}
+
 }  // extern "C"
+

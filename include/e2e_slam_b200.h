@@ -179,7 +179,8 @@ int e2e_geometric_fwd(const float *warped_depth, const float *interp_depth, cons
  *                         Outputs vertex_g, normal_g [H,W,3], alpha [H,W], valid [H,W] (uint8).
  *   e2e_fusion_associate  find_active_map_points + find_similar_map_points + find_best_unique_correspondences:
  *                         writes index_map [H,W] int64 (map point matched to each live pixel, -1 = none).
- *                         `keys` is an [H,W] uint64 scratch image.  The map size is read from the DEVICE
+ *                         `keys` is an [H,W] uint64 scratch image, `candidates` an int32 [n_upper] scratch array
+ *                         (pixel each map point competes for, -1 = none).  The map size is read from the DEVICE
  *                         int64 `n_map` (no host sync per step); `n_upper` >= *n_map only sizes the grid.
  *   e2e_fusion_merge_append fuse_with_map: confidence-weighted merge of matched map points in place, then
  *                         stream-compacted append (row-major pixel order) of valid unmatched live pixels at
@@ -198,7 +199,7 @@ int e2e_fusion_associate(const float *map_points, const float *map_normals, cons
                          const long long *n_map, long long n_upper,
                          const float *K, const float *pose, const float *vertex_g, const float *normal_g,
                          int H, int W, float dist_th, float dot_th,
-                         unsigned long long *keys, long long *index_map, void *stream);
+                         unsigned long long *keys, int *candidates, long long *index_map, void *stream);
 
 size_t e2e_fusion_workspace_bytes(int H, int W);
 
@@ -213,6 +214,17 @@ int e2e_fusion_merge_append(float *map_points, float *map_normals, float *map_co
  * routed to the live frame (grad_vertex_g, grad_rgb [H,W,3], grad_alpha [H,W], written) and, for matched
  * points, to the map that entered the step (grad_old_*; the caller pre-fills them with the pass-through
  * gradient of the unmatched points; NULL to skip).  Normals are not differentiated. */
+/* Whole-sequence fusion with known poses and no autograd (slam/custom_slam.py:26-34 with odom="gt"): the frame loop of
+ * rgbd_maps -> associate -> merge_append runs inside the library, one call per sequence.  depth [L,H,W], rgb [L,H,W,3],
+ * K [4,4], poses [L,4,4] (camera -> world); the map arrays need capacity >= n_upper + L*H*W; n_map is a device int64[2]
+ * (slot 0 = point count in / out, slot 1 = scratch). */
+size_t e2e_fusion_sequence_workspace_bytes(int H, int W, long long capacity);
+int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, const float *poses, int L, int H, int W,
+                        float sigma, float dist_th, float dot_th,
+                        float *map_points, float *map_normals, float *map_colors, float *map_ccount,
+                        long long *n_map, long long n_upper, long long capacity,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 int e2e_fusion_merge_append_bwd(const float *grad_points, const float *grad_colors, const float *grad_ccount,
                                 const float *old_points, const float *old_colors, const float *old_ccount,
                                 const float *vertex_g, const float *rgb, const float *alpha,

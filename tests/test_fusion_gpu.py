@@ -95,6 +95,30 @@ def test_fusion_call_full_sequence_invariants():
     assert bool(torch.isfinite(pc.points_list[0]).all())
 
 
+def test_sequence_call_equals_step_by_step():
+    """PointFusion.forward with known poses and no autograd runs the frame loop inside the library
+    (e2e_fusion_sequence); the map must be, bit for bit, the one the per-frame step() calls build."""
+    from e2e_slam_b200.slam import PointFusion, Pointclouds, RGBDImages
+    from e2e_slam_b200.synthetic import room_sequence
+    L, H, W = 12, 120, 160
+    depth, rgb, K, poses = room_sequence(L, H, W, device="cuda")
+    depth[:, 30:50, 60:90] = 0.0
+    rgbd = RGBDImages(rgb[None], depth[None, ..., None], K.view(1, 1, 4, 4), poses[None])
+    with torch.no_grad():
+        fast, out_poses = PointFusion(odom="gt", device="cuda")(rgbd)
+        slam = PointFusion(odom="gt", device="cuda")
+        pc = Pointclouds(device="cuda")
+        for s in range(L):
+            pc, _ = slam.step(pc, rgbd[:, s], inplace=True)
+    assert torch.equal(out_poses, poses[None])
+    for a, b in ((fast.points_list, pc.points_list), (fast.normals_list, pc.normals_list), (fast.colors_list, pc.colors_list),
+                 (fast.features_list, pc.features_list)):
+        assert a[0].shape == b[0].shape and torch.equal(a[0], b[0])
+    PointFusion(odom="gt", device="cuda").compact(fast)
+    assert fast._maps[0].pts.shape[0] == pc.points_list[0].shape[0]
+    assert torch.equal(fast.points_list[0], pc.points_list[0])
+
+
 def _torch_fuse(depth, rgb, K, pose, old, index_map, append_slot, sigma=0.6):
     """float64 torch restatement of one fusion step given the (integer) association, for autograd."""
     H, W = depth.shape
