@@ -28,6 +28,29 @@ def run(device, frames=60, H=480, W=640, repeats=3):
             launches = ops.launch_count() - l0
             n_final = int(pc._maps[0].n_dev.item())
     valid_px = int((depth > 0).sum().item())
+    # algorithmic bytes of the sequence: per frame 32*HW + 12*N + 16*A + 80*M + 40*U with N = map size before
+    # the frame, M = matched pixels, U = appended pixels, A (in-frustum candidates) taken as M (lower bound).  Collected from
+    # one untimed step-by-step pass.
+    from .slam import Pointclouds
+    alg = 0
+    with torch.no_grad():
+        pcs, n_prev = Pointclouds(device=device), 0
+        for s in range(frames):
+            pcs, _ = slam.step(pcs, rgbd[:, s], inplace=True)
+            index_map, slot = slam.last_association[0]
+            M, U = int((index_map >= 0).sum().item()), int((slot >= 0).sum().item())
+            alg += 32 * H * W + 12 * n_prev + 16 * M + 80 * M + 40 * U
+            n_prev += U
+    try:
+        import json, os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    ach = alg / (best * 1e-3) / 1e9
     return {"metric": "points fused/s", "value": valid_px / (best * 1e-3), "unit": "points/s", "frames": frames, "height": H, "width": W,
             "ms_per_sequence": best, "live_points": valid_px, "final_map_points": n_final, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_sequence": alg,
+                         "note": "small dependent kernels on a 300 k-pixel frame and a ~1 M-point map: latency-bound, not bandwidth-bound"},
             "config": "C3 fusion-60: PointFusion(odom='gt', dist_th=0.05, angle_th=20, sigma=0.6), synthetic room, best of %d" % repeats}
