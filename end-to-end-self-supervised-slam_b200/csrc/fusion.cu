@@ -58,19 +58,75 @@ __device__ __forceinline__ float dot3_lr(float a0, float a1, float a2, float b0,
     return xadd(xadd(xmul(a0, b0), xmul(a1, b1)), xmul(a2, b2));
 }
 
-// masked local vertex of pixel (y, x):  ((u*ifx + icx) * d, (v*ify + icy) * d, d) * [d > 0]
-__device__ __forceinline__ void local_vertex(const float *depth, int W, int y, int x, const Cam &c, float V[3], float &m)
+// masked local vertex of pixel (y, x) with depth d:  ((u*ifx + icx) * d, (v*ify + icy) * d, d) * [d > 0]
+__device__ __forceinline__ void local_vertex(float d, int y, int x, const Cam &c, float V[3], float &m)
 {
-    const float d = depth[y * W + x];
     m = (d > 0.0f) ? 1.0f : 0.0f;
     V[0] = xmul(xmul(xadd(xmul((float)x, c.ifx), c.icx), d), m);
     V[1] = xmul(xmul(xadd(xmul((float)y, c.ify), c.icy), d), m);
     V[2] = xmul(d, m);
 }
 
-// ---------------------------------------------------------------------------------------------
-// e2e_rgbd_maps
-// ---------------------------------------------------------------------------------------------
+// One pixel of the per-frame maps from its depth d and the depths of its right (dr) and lower (dd) neighbours
+// (forward differences; the last column / row has none).  Shared by rgbd_maps_kernel and the whole-sequence kernel.
+struct PixelMaps {
+    float vg[3], ng[3], alpha, valid;
+};
+
+__device__ __forceinline__ void rgbd_pixel_core(float d, float dr, float dd, int H, int W, int y, int x, const Cam &c,
+                                                float two_sigma2, PixelMaps &o)
+{
+    float V[3], Vr[3], Vd[3], m, mr, md;
+    local_vertex(d, y, x, c, V, m);
+    float dh[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
+    if (x + 1 < W) {
+        local_vertex(dr, y, x + 1, c, Vr, mr);
+#pragma unroll
+        for (int k = 0; k < 3; k++) dh[k] = xsub(Vr[k], V[k]);
+    }
+    if (y + 1 < H) {
+        local_vertex(dd, y + 1, x, c, Vd, md);
+#pragma unroll
+        for (int k = 0; k < 3; k++) dv[k] = xsub(Vd[k], V[k]);
+    }
+    float n[3];
+    n[0] = xsub(xmul(dh[1], dv[2]), xmul(dh[2], dv[1]));
+    n[1] = xsub(xmul(dh[2], dv[0]), xmul(dh[0], dv[2]));
+    n[2] = xsub(xmul(dh[0], dv[1]), xmul(dh[1], dv[0]));
+    float norm = __fsqrt_rn(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2])));
+    if (norm == 0.0f) norm = 1.0f;
+    float N[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) N[k] = xmul(xdiv(n[k], norm), m);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float vg = xadd(dot3_lr(c.R[k * 3], c.R[k * 3 + 1], c.R[k * 3 + 2], V[0], V[1], V[2]), c.t[k]);
+        o.vg[k] = xmul(vg, m);
+        o.ng[k] = dot3_lr(c.R[k * 3], c.R[k * 3 + 1], c.R[k * 3 + 2], N[0], N[1], N[2]);
+    }
+    // alpha = exp(-(X^2 + Y^2) / (2 sigma^2)): the float32 argument is exponentiated in double and
+    // rounded once, so host (numpy) and device agree on the bits of the confidence counts.
+    const float arg = -xdiv(xadd(xmul(V[0], V[0]), xmul(V[1], V[1])), two_sigma2);
+    o.alpha = (float)exp((double)arg);
+    o.valid = m;
+}
+
+__device__ __forceinline__ void rgbd_pixel(const float *depth, int H, int W, int i, const Cam &c, float two_sigma2,
+                                           float *vertex_g, float *normal_g, float *alpha, unsigned char *valid)
+{
+    const int y = i / W, x = i - y * W;
+    const float d = depth[i], dr = (x + 1 < W) ? depth[i + 1] : 0.0f, dd = (y + 1 < H) ? depth[i + W] : 0.0f;
+    PixelMaps o;
+    rgbd_pixel_core(d, dr, dd, H, W, y, x, c, two_sigma2, o);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        vertex_g[i * 3 + k] = o.vg[k];
+        normal_g[i * 3 + k] = o.ng[k];
+    }
+    alpha[i] = o.alpha;
+    valid[i] = (o.valid != 0.0f) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(FU_NT) rgbd_maps_kernel(const float *depth, const float *K, const float *pose, int H, int W,
                                                           float two_sigma2, float *vertex_g, float *normal_g, float *alpha,
                                                           unsigned char *valid)
@@ -78,42 +134,8 @@ __global__ void __launch_bounds__(FU_NT) rgbd_maps_kernel(const float *depth, co
     __shared__ Cam c;
     stage_cam(K, pose, &c);
     const int HW = H * W;
-    for (int i = blockIdx.x * FU_NT + threadIdx.x; i < HW; i += gridDim.x * FU_NT) {
-        const int y = i / W, x = i - y * W;
-        float V[3], Vr[3], Vd[3], m, mr, md;
-        local_vertex(depth, W, y, x, c, V, m);
-        float dh[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
-        if (x + 1 < W) {
-            local_vertex(depth, W, y, x + 1, c, Vr, mr);
-#pragma unroll
-            for (int k = 0; k < 3; k++) dh[k] = xsub(Vr[k], V[k]);
-        }
-        if (y + 1 < H) {
-            local_vertex(depth, W, y + 1, x, c, Vd, md);
-#pragma unroll
-            for (int k = 0; k < 3; k++) dv[k] = xsub(Vd[k], V[k]);
-        }
-        float n[3];
-        n[0] = xsub(xmul(dh[1], dv[2]), xmul(dh[2], dv[1]));
-        n[1] = xsub(xmul(dh[2], dv[0]), xmul(dh[0], dv[2]));
-        n[2] = xsub(xmul(dh[0], dv[1]), xmul(dh[1], dv[0]));
-        float norm = __fsqrt_rn(xadd(xadd(xmul(n[0], n[0]), xmul(n[1], n[1])), xmul(n[2], n[2])));
-        if (norm == 0.0f) norm = 1.0f;
-        float N[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) N[k] = xmul(xdiv(n[k], norm), m);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float vg = xadd(dot3_lr(c.R[k * 3], c.R[k * 3 + 1], c.R[k * 3 + 2], V[0], V[1], V[2]), c.t[k]);
-            vertex_g[i * 3 + k] = xmul(vg, m);
-            normal_g[i * 3 + k] = dot3_lr(c.R[k * 3], c.R[k * 3 + 1], c.R[k * 3 + 2], N[0], N[1], N[2]);
-        }
-        // alpha = exp(-(X^2 + Y^2) / (2 sigma^2)): the float32 argument is exponentiated in double and
-        // rounded once, so host (numpy) and device agree on the bits of the confidence counts.
-        const float arg = -xdiv(xadd(xmul(V[0], V[0]), xmul(V[1], V[1])), two_sigma2);
-        alpha[i] = (float)exp((double)arg);
-        valid[i] = (m != 0.0f) ? 1 : 0;
-    }
+    for (int i = blockIdx.x * FU_NT + threadIdx.x; i < HW; i += gridDim.x * FU_NT)
+        rgbd_pixel(depth, H, W, i, c, two_sigma2, vertex_g, normal_g, alpha, valid);
 }
 
 // d(vertex_g, alpha)/d depth.  Normals carry no gradient (no loss in the reference reads them).
@@ -162,6 +184,53 @@ struct AssocParams {
     int *cand;
 };
 
+// Steps 1-3 of the association for one map point, split at the two memory round trips.
+//   assoc_pixel    active map points: into the live camera, in front, inside the frustum, rounded to a pixel (-1 = inactive)
+//   assoc_key      similar (close in space, similar normal) -> the 64-bit key (1/(c + 1e-20), dist^2) it competes with
+struct AssocConst {
+    int H, W;
+    float dist_th, dot_th, u_hi, v_hi;
+};
+
+__device__ __forceinline__ int assoc_pixel(const Cam &c, const AssocConst &a, float px, float py, float pz)
+{
+    const float qx = xadd(dot3_lr(c.Ri[0], c.Ri[1], c.Ri[2], px, py, pz), c.ti[0]);
+    const float qy = xadd(dot3_lr(c.Ri[3], c.Ri[4], c.Ri[5], px, py, pz), c.ti[1]);
+    const float qz = xadd(dot3_lr(c.Ri[6], c.Ri[7], c.Ri[8], px, py, pz), c.ti[2]);
+    if (!(qz > 0.0f)) return -1;
+    const float h0 = xadd(dot3_lr(c.K[0], c.K[1], c.K[2], qx, qy, qz), c.K[3]);
+    const float h1 = xadd(dot3_lr(c.K[4], c.K[5], c.K[6], qx, qy, qz), c.K[7]);
+    const float h2 = xadd(dot3_lr(c.K[8], c.K[9], c.K[10], qx, qy, qz), c.K[11]);
+    const float u = xdiv(h0, h2), v = xdiv(h1, h2);
+    if (!(u > -1e-3f && u < a.u_hi && v > -1e-3f && v < a.v_hi)) return -1;
+    int w = __float2int_rn(u), h = __float2int_rn(v);       // round half to even, like torch.round
+    w = min(max(w, 0), a.W - 1);
+    h = min(max(h, 0), a.H - 1);
+    return h * a.W + w;
+}
+
+__device__ __forceinline__ unsigned long long assoc_make_key(float cc, float dist2)
+{
+    const float inv_c = xdiv(1.0f, xadd(cc, 1e-20f));
+    return ((unsigned long long)__float_as_uint(inv_c) << 32) | (unsigned long long)__float_as_uint(dist2);
+}
+
+__device__ __forceinline__ float assoc_dist2(float vx, float vy, float vz, float px, float py, float pz)
+{
+    const float dx = xsub(vx, px), dy = xsub(vy, py), dz = xsub(vz, pz);
+    return xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+}
+
+__device__ __forceinline__ bool assoc_key(const AssocConst &a, float px, float py, float pz, float nx, float ny, float nz, float cc,
+                                          float vx, float vy, float vz, float gx, float gy, float gz, unsigned long long &key)
+{
+    const float dist2 = assoc_dist2(vx, vy, vz, px, py, pz);
+    const float dot = dot3_lr(gx, gy, gz, nx, ny, nz);
+    if (!(__fsqrt_rn(dist2) < a.dist_th && dot > a.dot_th)) return false;
+    key = assoc_make_key(cc, dist2);        // best unique: lexicographic minimum of (1/(c + 1e-20), dist^2, n) per pixel
+    return true;
+}
+
 // Pass 1: every map point is projected into the live frame; candidates (in the frustum, close in space, similar
 // normal) race for their pixel with a 64-bit atomicMin of the key (1/(c+1e-20), dist^2) and remember their pixel in
 // cand[n] (-1 = not a candidate).  All per-point loads (point, normal, confidence) are issued up front, so the
@@ -170,39 +239,21 @@ __global__ void __launch_bounds__(FU_NT) associate_pass1_kernel(const AssocParam
 {
     __shared__ Cam c;
     stage_cam(p.K, p.pose, &c);
+    const AssocConst a{p.H, p.W, p.dist_th, p.dot_th, p.u_hi, p.v_hi};
     const long long N = *p.n_map;
     for (long long n = (long long)blockIdx.x * FU_NT + threadIdx.x; n < N; n += (long long)gridDim.x * FU_NT) {
         const float px = p.pts[n * 3], py = p.pts[n * 3 + 1], pz = p.pts[n * 3 + 2];
         const float nx = p.nrm[n * 3], ny = p.nrm[n * 3 + 1], nz = p.nrm[n * 3 + 2];
         const float cc = p.cc[n];
         int cand = -1;
-        // 1. active map points: into the live camera, in front, inside the frustum, round to a pixel
-        const float qx = xadd(dot3_lr(c.Ri[0], c.Ri[1], c.Ri[2], px, py, pz), c.ti[0]);
-        const float qy = xadd(dot3_lr(c.Ri[3], c.Ri[4], c.Ri[5], px, py, pz), c.ti[1]);
-        const float qz = xadd(dot3_lr(c.Ri[6], c.Ri[7], c.Ri[8], px, py, pz), c.ti[2]);
-        if (qz > 0.0f) {
-            const float h0 = xadd(dot3_lr(c.K[0], c.K[1], c.K[2], qx, qy, qz), c.K[3]);
-            const float h1 = xadd(dot3_lr(c.K[4], c.K[5], c.K[6], qx, qy, qz), c.K[7]);
-            const float h2 = xadd(dot3_lr(c.K[8], c.K[9], c.K[10], qx, qy, qz), c.K[11]);
-            const float u = xdiv(h0, h2), v = xdiv(h1, h2);
-            if (u > -1e-3f && u < p.u_hi && v > -1e-3f && v < p.v_hi) {
-                int w = __float2int_rn(u), h = __float2int_rn(v);       // round half to even, like torch.round
-                w = min(max(w, 0), p.W - 1);
-                h = min(max(h, 0), p.H - 1);
-                const int pix = h * p.W + w;
-                // 2. similar: close in space, similar normal (both live-frame gathers issued together)
-                const float vx = p.vertex_g[pix * 3], vy = p.vertex_g[pix * 3 + 1], vz = p.vertex_g[pix * 3 + 2];
-                const float gx = p.normal_g[pix * 3], gy = p.normal_g[pix * 3 + 1], gz = p.normal_g[pix * 3 + 2];
-                const float dx = xsub(vx, px), dy = xsub(vy, py), dz = xsub(vz, pz);
-                const float dist2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-                const float dot = dot3_lr(gx, gy, gz, nx, ny, nz);
-                if (__fsqrt_rn(dist2) < p.dist_th && dot > p.dot_th) {
-                    // 3. best unique: lexicographic minimum of (1/(c + 1e-20), dist^2, n) per pixel
-                    const float inv_c = xdiv(1.0f, xadd(cc, 1e-20f));
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(inv_c) << 32) | (unsigned long long)__float_as_uint(dist2);
-                    atomicMin(p.keys + pix, key);
-                    cand = pix;
-                }
+        const int pix = assoc_pixel(c, a, px, py, pz);
+        if (pix >= 0) {
+            const float vx = p.vertex_g[pix * 3], vy = p.vertex_g[pix * 3 + 1], vz = p.vertex_g[pix * 3 + 2];
+            const float gx = p.normal_g[pix * 3], gy = p.normal_g[pix * 3 + 1], gz = p.normal_g[pix * 3 + 2];
+            unsigned long long key;
+            if (assoc_key(a, px, py, pz, nx, ny, nz, cc, vx, vy, vz, gx, gy, gz, key)) {
+                atomicMin(p.keys + pix, key);
+                cand = pix;
             }
         }
         p.cand[n] = cand;
@@ -218,10 +269,8 @@ __global__ void __launch_bounds__(FU_NT) associate_pass2_kernel(const AssocParam
         const int pix = p.cand[n];
         if (pix < 0) continue;
         const float px = p.pts[n * 3], py = p.pts[n * 3 + 1], pz = p.pts[n * 3 + 2];
-        const float dx = xsub(p.vertex_g[pix * 3], px), dy = xsub(p.vertex_g[pix * 3 + 1], py), dz = xsub(p.vertex_g[pix * 3 + 2], pz);
-        const float dist2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-        const float inv_c = xdiv(1.0f, xadd(p.cc[n], 1e-20f));
-        const unsigned long long key = ((unsigned long long)__float_as_uint(inv_c) << 32) | (unsigned long long)__float_as_uint(dist2);
+        const float dist2 = assoc_dist2(p.vertex_g[pix * 3], p.vertex_g[pix * 3 + 1], p.vertex_g[pix * 3 + 2], px, py, pz);
+        const unsigned long long key = assoc_make_key(p.cc[n], dist2);
         if (p.keys[pix] == key) atomicMin(p.index_map + pix, (unsigned long long)n);
     }
 }
@@ -242,6 +291,35 @@ struct FuseParams {
     int nchunks;
 };
 
+__device__ __forceinline__ float merge_val(float c, float o, float a, float f, float den)
+{
+    return xdiv(xadd(xmul(c, o), xmul(a, f)), den);
+}
+
+// (c*old + a*new) / (c + a) for point, normal and colour of map entry n from live pixel i, one rounding per operation.
+// All twenty loads are issued before the first store (the arrays may alias as far as the compiler knows, so
+// interleaving loads and stores would serialise nine memory round trips).
+__device__ __forceinline__ void merge_point(float *pts, float *nrm, float *col, float *ccount, long long n,
+                                            const float *vertex_g, const float *normal_g, const float *rgb, const float *alpha, int i)
+{
+    const float c = ccount[n], a = alpha[i];
+    float o[9], f[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        o[j] = pts[n * 3 + j]; o[3 + j] = nrm[n * 3 + j]; o[6 + j] = col[n * 3 + j];
+        f[j] = vertex_g[i * 3 + j]; f[3 + j] = normal_g[i * 3 + j]; f[6 + j] = rgb[i * 3 + j];
+    }
+    const float den = xadd(c, a);
+    float r[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) r[j] = merge_val(c, o[j], a, f[j], den);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        pts[n * 3 + j] = r[j]; nrm[n * 3 + j] = r[3 + j]; col[n * 3 + j] = r[6 + j];
+    }
+    ccount[n] = den;
+}
+
 __global__ void __launch_bounds__(FU_NT) fuse_merge_count_kernel(const FuseParams p)
 {
     __shared__ int wsum[FU_NT / 32];
@@ -254,15 +332,7 @@ __global__ void __launch_bounds__(FU_NT) fuse_merge_count_kernel(const FuseParam
         if (i >= HW) continue;
         const long long n = p.index_map[i];
         if (n >= 0) {
-            const float c = p.cc[n], a = p.alpha[i];
-            const float den = xadd(c, a);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {       // (c*old + a*new) / (c + a), one rounding per operation
-                p.pts[n * 3 + j] = xdiv(xadd(xmul(c, p.pts[n * 3 + j]), xmul(a, p.vertex_g[i * 3 + j])), den);
-                p.nrm[n * 3 + j] = xdiv(xadd(xmul(c, p.nrm[n * 3 + j]), xmul(a, p.normal_g[i * 3 + j])), den);
-                p.col[n * 3 + j] = xdiv(xadd(xmul(c, p.col[n * 3 + j]), xmul(a, p.rgb[i * 3 + j])), den);
-            }
-            p.cc[n] = den;
+            merge_point(p.pts, p.nrm, p.col, p.cc, n, p.vertex_g, p.normal_g, p.rgb, p.alpha, i);
         } else if (p.valid[i]) {
             cnt++;
         }
@@ -414,6 +484,401 @@ __global__ void __launch_bounds__(FU_NT) fuse_bwd_kernel(const FuseBwdParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Whole-sequence kernel: ONE cooperative launch fuses all L frames.  Every CTA is resident (cooperative
+// launch), the phases of a frame are separated by a grid-wide barrier instead of a kernel boundary:
+//
+//   prologue   map [n,3] arrays -> float4 working map, maps(0)                        | barrier
+//   frame s    P1  every map point: project, compare, 128-bit compare-and-swap minimum of (key, map index)  | barrier
+//              P3  pixels, a contiguous range per CTA: merge matched map points, count the valid unmatched
+//                  ones, publish the count, maps(s+1) into the other buffer set while the counts of the
+//                  preceding CTAs arrive, append in row-major pixel order, last CTA writes the new size  | barrier
+//   epilogue   float4 working map -> the caller's [n,3] arrays
+//
+// Two barriers per frame (2-3 us each) replace nine stream operations.  Inside the kernel the map and
+// the per-frame maps are float4 records ({x,y,z,ccount}, {nx,ny,nz,-}, {r,g,b,-}; {vx,vy,vz,alpha}, {nx,ny,nz,valid}):
+// a [n,3] fp32 array costs three 12-sector requests per warp access, a float4 record one 16-sector request,
+// and these phases are bound by exactly that request rate.  The arithmetic is that of the per-frame kernels
+// above (same device functions), so the map is the same bit for bit.
+// ---------------------------------------------------------------------------------------------
+#ifndef E2E_SEQ_NT
+#define E2E_SEQ_NT 576                  // 2 CTAs/SM x 576 threads x 148 SMs >= 480*640 / 2: two pixels per thread in P3
+#endif
+constexpr int SEQ_NT = E2E_SEQ_NT;
+constexpr int SEQ_NW = SEQ_NT / 32;
+constexpr int SEQ_MAX_ITERS = 32;       // pixel sub-blocks of SEQ_NT per CTA in P3 (one flag bit each)
+
+// 128-bit association record of a pixel: hi = (1/(c + 1e-20), dist^2) as in the two-pass kernels, lo = map index.  The
+// lexicographic minimum over (hi, lo) is exactly what pass 1 + pass 2 select, so ONE compare-and-swap loop per candidate
+// (atom.cas.b128, sm_90+) replaces the second pass over the candidates and its grid barrier.
+struct __align__(16) Key128 {
+    unsigned long long lo, hi;
+};
+
+__device__ __forceinline__ Key128 cas128(Key128 *addr, Key128 expect, Key128 val)
+{
+    Key128 old;
+    asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+                 "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old.lo), "=l"(old.hi)
+                 : "l"(expect.lo), "l"(expect.hi), "l"(val.lo), "l"(val.hi), "l"(addr)
+                 : "memory");
+    return old;
+}
+
+struct SeqParams {
+    const float *depth, *rgb, *K, *poses;
+    int L, H, W;
+    float two_sigma2;
+    AssocConst ac;
+    float *pts, *nrm, *col, *cc;        // the caller's map arrays (read in the prologue, written in the epilogue)
+    long long *n_map;
+    long long capacity;
+    float4 *pts4, *nrm4, *col4;         // working map
+    float4 *vg4[2], *ng4[2];            // per-frame maps, two buffer sets
+    Key128 *keys[2];                    // per pixel: the best candidate's (key, map index), all ones = none
+    unsigned long long *counts;         // [gridDim.x] (frame + 1) << 32 | appended pixels of the CTA
+    unsigned *barrier;                  // `go` word of the grid barrier (per-CTA arrival slots live at counts + 1024)
+};
+
+// The per-CTA append counts travel in ONE word together with their frame tag and nothing else is read on their strength,
+// so relaxed accesses are enough (a release store would first wait for the CTA's merge stores to drain, ~1.5 us).
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+#ifdef E2E_SEQ_TIMING
+__device__ __forceinline__ void seq_stamp(const unsigned long long *counts, int idx)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const_cast<unsigned long long *>(counts)[2048 + idx] = t;
+    }
+}
+#define SEQ_STAMP(i) seq_stamp(p.counts, (i))
+__device__ __forceinline__ void seq_stamp3(const unsigned long long *counts, int idx)
+{
+    const int which = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1));
+    if (which >= 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const_cast<unsigned long long *>(counts)[2048 + 512 + which * 128 + idx] = t;
+    }
+}
+#define SEQ_STAMP3(i) seq_stamp3(p.counts, (i))
+#else
+#define SEQ_STAMP(i)
+#define SEQ_STAMP3(i)
+#endif
+
+// Grid-wide barrier (all CTAs are co-resident: cooperative launch) without a contended atomic: 296 same-address atomics
+// serialise at ~27 cycles each in L2 (4 us per barrier, measured).  Every CTA release-stores the barrier's epoch into its
+// own slot; warp 0 of CTA 0 polls all slots (a few per lane, loads batched), fences and release-stores the epoch into `go`; thread 0 of
+// every other CTA polls `go` and fences (acquire side; the fence also drops the SM's stale L1 lines before the next phase).
+// Release is cumulative over the CTA's writes because it follows bar.sync.  No sequentially-consistent fence anywhere
+// (__threadfence() is MEMBAR.SC.GPU).
+__device__ __forceinline__ void grid_barrier(unsigned *go, unsigned *slots, unsigned &epoch)
+{
+    __syncthreads();
+    epoch++;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            // each lane watches every 32nd slot, eight independent loads per round trip (a serial poll of ~10 slots per
+            // lane costs ~0.3 us each)
+            for (unsigned b0 = 1 + threadIdx.x; b0 < gridDim.x; b0 += 32 * 8) {
+                bool all;
+                do {
+                    all = true;
+                    unsigned g[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const unsigned b = b0 + 32 * j;
+                        g[j] = epoch;
+                        if (b < gridDim.x) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g[j]) : "l"(slots + b) : "memory");
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) all &= (int)(g[j] - epoch) >= 0;
+                } while (!all);
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            __syncwarp();
+            if (threadIdx.x == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(epoch) : "memory");   // after the fence: a release pattern
+        }
+    } else if (threadIdx.x == 0) {
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(slots + blockIdx.x), "r"(epoch) : "memory");
+        unsigned g;
+        do asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(go) : "memory");
+        while ((int)(g - epoch) < 0);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// maps(f): the CTA's pixel range, two pixels per thread and trip with all six depth loads issued first.
+template <int SB>
+__device__ __forceinline__ void seq_maps(const SeqParams &p, int f, const Cam &c, int pix0, int chunk, int iters)
+{
+    constexpr int sb = SB;
+    const int HW = p.H * p.W;
+    const float *depth = p.depth + (size_t)f * HW;
+    float4 *vg4 = p.vg4[SB], *ng4 = p.ng4[SB];
+    Key128 *keys = p.keys[SB];
+    for (int k0 = 0; k0 < iters; k0 += 2) {
+        int i[2], y[2], x[2];
+        bool on[2];
+        float d[2], dr[2], dd[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int r = (k0 + e) * SEQ_NT + threadIdx.x;
+            i[e] = pix0 + r;
+            on[e] = (k0 + e < iters) && r < chunk && i[e] < HW;
+            y[e] = on[e] ? i[e] / p.W : 0;
+            x[e] = on[e] ? i[e] - y[e] * p.W : 0;
+            d[e] = on[e] ? depth[i[e]] : 0.0f;
+            dr[e] = (on[e] && x[e] + 1 < p.W) ? depth[i[e] + 1] : 0.0f;
+            dd[e] = (on[e] && y[e] + 1 < p.H) ? depth[i[e] + p.W] : 0.0f;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (!on[e]) continue;
+            PixelMaps o;
+            rgbd_pixel_core(d[e], dr[e], dd[e], p.H, p.W, y[e], x[e], c, p.two_sigma2, o);
+            vg4[i[e]] = make_float4(o.vg[0], o.vg[1], o.vg[2], o.alpha);
+            ng4[i[e]] = make_float4(o.ng[0], o.ng[1], o.ng[2], o.valid);
+            keys[i[e]] = Key128{~0ull, ~0ull};
+        }
+    }
+}
+
+struct SeqShared {
+    Cam cams[2];
+    int wcnt[SEQ_MAX_ITERS * SEQ_NW];      // appended pixels per (sub-block, warp), then exclusive offsets
+    long long sh_base;
+};
+
+// One frame; SB = s & 1 selects the buffer set at compile time (the pointers stay in the constant bank).
+template <int SB>
+__device__ __forceinline__ void seq_frame(const SeqParams &p, SeqShared &sh, int s, unsigned &target, int pix0, int chunk, int iters)
+{
+    constexpr int sb = SB;
+    Cam *cams = sh.cams;
+    int *wcnt = sh.wcnt;
+    long long &sh_base = sh.sh_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int HW = p.H * p.W;
+    const long long gtid = (long long)blockIdx.x * SEQ_NT + tid, gthreads = (long long)gridDim.x * SEQ_NT;
+    const Cam &c = cams[sb];
+    const float4 *vg4 = p.vg4[SB], *ng4 = p.ng4[SB];
+    Key128 *keys = p.keys[SB];
+    const long long N = *reinterpret_cast<volatile long long *>(p.n_map);
+    if (tid == 32) {                                        // off the critical path: next frame's camera, next counter
+        if (s + 1 < p.L) build_cam(p.K, p.poses + (size_t)(s + 1) * 16, cams[sb ^ 1]);
+    }
+
+    // ---- P1: one map point per thread and trip.  The next trip's point is loaded before this trip's gathers are used, and
+    // the compare-and-swap of a candidate is only looked at one trip later, so neither round trip stalls the thread.
+    {
+        long long n = gtid;
+        float4 nxt = (n < N) ? p.pts4[n] : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool pending = false;
+        int ppix = 0;
+        Key128 mine{0ull, 0ull}, seen{0ull, 0ull}, old{0ull, 0ull};
+        // a failed attempt returns what is there; the candidate retries only while it is smaller (rare: most pixels see one
+        // candidate, and the first attempt expects the initial all-ones record)
+        auto resolve = [&]() {
+            while (!(old.hi == seen.hi && old.lo == seen.lo)) {
+                seen = old;
+                if (!(mine.hi < seen.hi || (mine.hi == seen.hi && mine.lo < seen.lo))) break;
+                old = cas128(keys + ppix, seen, mine);
+            }
+            pending = false;
+        };
+        for (; n < N; n += gthreads) {
+            const float4 cur = nxt;
+            const int pix = assoc_pixel(c, p.ac, cur.x, cur.y, cur.z);
+            float4 nr, lv, ln;
+            if (pix >= 0) {
+                nr = p.nrm4[n];
+                lv = vg4[pix];
+                ln = ng4[pix];
+            }
+            if (n + gthreads < N) nxt = p.pts4[n + gthreads];
+            if (pending) resolve();
+            unsigned long long key = 0ull;
+            if (pix >= 0 && assoc_key(p.ac, cur.x, cur.y, cur.z, nr.x, nr.y, nr.z, cur.w, lv.x, lv.y, lv.z, ln.x, ln.y, ln.z, key)) {
+                mine = Key128{(unsigned long long)n, key};
+                seen = Key128{~0ull, ~0ull};
+                ppix = pix;
+                old = cas128(keys + ppix, seen, mine);
+                pending = true;
+            }
+        }
+        if (pending) resolve();
+    }
+    grid_barrier(p.barrier, reinterpret_cast<unsigned *>(p.counts + 1024), target);
+    SEQ_STAMP(2 + 3 * s);
+    SEQ_STAMP(3 + 3 * s);
+
+    // ---- P3 ------------------------------------------------------------------------------------------
+    const float *rgb = p.rgb + (size_t)s * HW * 3;
+    unsigned flags = 0u;                                   // bit k: this thread's pixel of sub-block k is appended
+    for (int k0 = 0; k0 < iters; k0 += 2) {
+        int i[2];
+        bool on[2];
+        unsigned n[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {                       // both index-map loads first
+            const int r = (k0 + e) * SEQ_NT + tid;
+            i[e] = pix0 + r;
+            on[e] = (k0 + e < iters) && r < chunk && i[e] < HW;
+            n[e] = on[e] ? (unsigned)keys[i[e]].lo : 0xffffffffu;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            bool flag = false;
+            if (n[e] != 0xffffffffu) {
+                const float4 mp = p.pts4[n[e]], mn = p.nrm4[n[e]], mc = p.col4[n[e]];
+                const float4 lv = vg4[i[e]], ln = ng4[i[e]];
+                const float r = rgb[i[e] * 3], g = rgb[i[e] * 3 + 1], bl = rgb[i[e] * 3 + 2];
+                const float cw = mp.w, a = lv.w, den = xadd(cw, a);
+                p.pts4[n[e]] = make_float4(merge_val(cw, mp.x, a, lv.x, den), merge_val(cw, mp.y, a, lv.y, den),
+                                           merge_val(cw, mp.z, a, lv.z, den), den);
+                p.nrm4[n[e]] = make_float4(merge_val(cw, mn.x, a, ln.x, den), merge_val(cw, mn.y, a, ln.y, den),
+                                           merge_val(cw, mn.z, a, ln.z, den), 0.0f);
+                p.col4[n[e]] = make_float4(merge_val(cw, mc.x, a, r, den), merge_val(cw, mc.y, a, g, den),
+                                           merge_val(cw, mc.z, a, bl, den), 0.0f);
+            } else if (on[e]) {
+                flag = ng4[i[e]].w != 0.0f;
+            }
+            if (k0 + e < iters) {
+                const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+                if (flag) flags |= 1u << (k0 + e);
+                if (lane == 0) wcnt[(k0 + e) * SEQ_NW + wid] = __popc(ballot);
+            }
+        }
+    }
+    __syncthreads();
+    SEQ_STAMP(256 + 4 * s);
+    if (wid == 0) {                                        // exclusive scan of wcnt in (sub-block, warp) order = pixel order
+        int carry = 0;
+        for (int b0 = 0; b0 < iters * SEQ_NW; b0 += 32) {
+            const int v = (b0 + lane < iters * SEQ_NW) ? wcnt[b0 + lane] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b0 + lane < iters * SEQ_NW) wcnt[b0 + lane] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) st_relaxed_u64(p.counts + blockIdx.x, ((unsigned long long)(s + 1) << 32) | (unsigned)carry);
+    }
+    __syncthreads();
+    SEQ_STAMP(257 + 4 * s);
+    if (s + 1 < p.L) seq_maps<SB ^ 1>(p, s + 1, cams[sb ^ 1], pix0, chunk, iters);   // independent of the map: fills the wait for the other CTAs
+    SEQ_STAMP(258 + 4 * s);
+    if (wid == 0) {                                        // sum of the counts of all preceding CTAs (same frame tag)
+        long long before = 0;
+        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+            unsigned long long v;
+            do v = ld_relaxed_u64(p.counts + b);
+            while ((unsigned)(v >> 32) != (unsigned)(s + 1));
+            before += (long long)(unsigned)v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        if (lane == 0) sh_base = N + before;
+    }
+    __syncthreads();
+    SEQ_STAMP(259 + 4 * s);
+    const long long base = sh_base;
+    for (int k = 0; k < iters; k++) {
+        const bool flag = (flags >> k) & 1u;
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+        if (flag) {
+            const int i = pix0 + k * SEQ_NT + tid;
+            const long long slot = base + wcnt[k * SEQ_NW + wid] + __popc(ballot & ((1u << lane) - 1));
+            if (slot < p.capacity) {
+                const float4 lv = vg4[i], ln = ng4[i];
+                const float r = rgb[i * 3], g = rgb[i * 3 + 1], bl = rgb[i * 3 + 2];
+                p.pts4[slot] = lv;                                     // {vertex, alpha}: alpha is the new point's confidence
+                p.nrm4[slot] = make_float4(ln.x, ln.y, ln.z, 0.0f);
+                p.col4[slot] = make_float4(r, g, bl, 0.0f);
+            }
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        // total = everything before the last CTA + its own count
+        const unsigned long long own = ld_relaxed_u64(p.counts + blockIdx.x);
+        long long total = base + (long long)(unsigned)own;
+        if (total > p.capacity) total = p.capacity;
+        *reinterpret_cast<volatile long long *>(p.n_map) = total;
+    }
+    grid_barrier(p.barrier, reinterpret_cast<unsigned *>(p.counts + 1024), target);
+    SEQ_STAMP(4 + 3 * s);
+}
+
+__global__ void __launch_bounds__(SEQ_NT, 2) fusion_sequence_kernel(const SeqParams p)
+{
+    __shared__ SeqShared sh;
+    Cam *cams = sh.cams;
+    const int tid = threadIdx.x;
+    const int HW = p.H * p.W;
+    const int chunk = (HW + gridDim.x - 1) / gridDim.x;       // contiguous pixels per CTA in P3
+    const int iters = (chunk + SEQ_NT - 1) / SEQ_NT;
+    const int pix0 = blockIdx.x * chunk;
+    const long long gtid = (long long)blockIdx.x * SEQ_NT + tid, gthreads = (long long)gridDim.x * SEQ_NT;
+    unsigned target = 0;
+
+#ifdef E2E_SEQ_TIMING
+    for (int j = 0; j < 16; j++) {
+        SEQ_STAMP(1024 + j);
+        grid_barrier(p.barrier, reinterpret_cast<unsigned *>(p.counts + 1024), target);
+    }
+    SEQ_STAMP(1024 + 16);
+#endif
+    SEQ_STAMP(0);
+    if (tid == 0) {
+        build_cam(p.K, p.poses, cams[0]);
+    }
+    {   // the caller's map (if any) -> working records
+        const long long N0 = *reinterpret_cast<volatile long long *>(p.n_map);
+        for (long long n = gtid; n < N0; n += gthreads) {
+            p.pts4[n] = make_float4(p.pts[n * 3], p.pts[n * 3 + 1], p.pts[n * 3 + 2], p.cc[n]);
+            p.nrm4[n] = make_float4(p.nrm[n * 3], p.nrm[n * 3 + 1], p.nrm[n * 3 + 2], 0.0f);
+            p.col4[n] = make_float4(p.col[n * 3], p.col[n * 3 + 1], p.col[n * 3 + 2], 0.0f);
+        }
+    }
+    __syncthreads();
+    seq_maps<0>(p, 0, cams[0], pix0, chunk, iters);
+    grid_barrier(p.barrier, reinterpret_cast<unsigned *>(p.counts + 1024), target);
+    SEQ_STAMP(1);
+
+    for (int s = 0; s < p.L; s++) {
+        if (s & 1) seq_frame<1>(p, sh, s, target, pix0, chunk, iters);
+        else seq_frame<0>(p, sh, s, target, pix0, chunk, iters);
+    }
+
+    // ---- epilogue: working records -> the caller's [n,3] arrays -----------------------------------------
+    const long long N = *reinterpret_cast<volatile long long *>(p.n_map);
+    for (long long n = gtid; n < N; n += gthreads) {
+        const float4 a = p.pts4[n], b = p.nrm4[n], cl = p.col4[n];
+        p.pts[n * 3] = a.x; p.pts[n * 3 + 1] = a.y; p.pts[n * 3 + 2] = a.z;
+        p.nrm[n * 3] = b.x; p.nrm[n * 3 + 1] = b.y; p.nrm[n * 3 + 2] = b.z;
+        p.col[n * 3] = cl.x; p.col[n * 3 + 1] = cl.y; p.col[n * 3 + 2] = cl.z;
+        p.cc[n] = a.w;
+    }
+}
+
 static inline int grid_for(long long n)
 {
     long long b = (n + FU_NT - 1) / FU_NT;
@@ -539,24 +1004,48 @@ int e2e_fusion_merge_append_bwd(const float *grad_points, const float *grad_colo
  * --------------------------------------------------------------------------------------------- */
 static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 
-size_t e2e_fusion_sequence_workspace_bytes(int H, int W, long long capacity)
+// Grid of the whole-sequence kernel: every CTA must be resident (cooperative launch).  0 = not available.
+static int sequence_grid()
 {
-    const size_t hw = (size_t)H * W;
+    static int grid = -1;
+    if (grid >= 0) return grid;
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fusion_sequence_kernel, SEQ_NT, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;                       // not cached: a later call on a working context may succeed
+    }
+    grid = coop ? sms * per_sm : 0;
+    return grid;
+}
+
+static size_t sequence_loop_bytes(size_t hw, long long capacity, int H, int W)
+{
     return align256(hw * 12) * 2 + align256(hw * 4) + align256(hw) + align256(hw * 8) * 2 + align256((size_t)capacity * 4) +
            align256(e2e_fusion_workspace_bytes(H, W)) + 256;
 }
 
-int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, const float *poses, int L, int H, int W,
-                        float sigma, float dist_th, float dot_th,
-                        float *map_points, float *map_normals, float *map_colors, float *map_ccount,
-                        long long *n_map, long long n_upper, long long capacity,
-                        void *workspace, size_t workspace_bytes, void *stream)
+static size_t sequence_coop_bytes(size_t hw, long long capacity)
 {
-    E2E_REQUIRE(depth && rgb && K && poses && map_points && map_normals && map_colors && map_ccount && n_map && workspace,
-                "fusion_sequence: null argument");
-    E2E_REQUIRE(L >= 0 && H > 0 && W > 0 && n_upper >= 0, "fusion_sequence: bad sizes");
-    E2E_REQUIRE(capacity >= n_upper + (long long)L * H * W, "fusion_sequence: capacity must be >= n_upper + L*H*W");
-    E2E_REQUIRE(workspace_bytes >= e2e_fusion_sequence_workspace_bytes(H, W, capacity), "fusion_sequence: workspace too small");
+    // working map (3 float4 records per point), two buffer sets of {vertex+alpha, normal+valid, association record},
+    // per-CTA counts / barrier slots / timing stamps, barrier word
+    return 3 * align256((size_t)capacity * 16) + 2 * align256(hw * 16) * 3 + align256(8 * 4096) + 256;
+}
+
+size_t e2e_fusion_sequence_workspace_bytes(int H, int W, long long capacity)
+{
+    const size_t hw = (size_t)H * W;
+    const size_t a = sequence_loop_bytes(hw, capacity, H, W), b = sequence_coop_bytes(hw, capacity);
+    return a > b ? a : b;
+}
+
+// The per-frame loop over the stand-alone entry points (also the reference the cooperative kernel is tested against).
+static int fusion_sequence_loop(const float *depth, const float *rgb, const float *K, const float *poses, int L, int H, int W,
+                                float sigma, float dist_th, float dot_th,
+                                float *map_points, float *map_normals, float *map_colors, float *map_ccount,
+                                long long *n_map, long long n_upper, long long capacity, void *workspace, void *stream)
+{
     const size_t hw = (size_t)H * W;
     unsigned char *w = (unsigned char *)workspace;
     float *vg = (float *)w;                                 w += align256(hw * 12);
@@ -582,6 +1071,59 @@ int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, co
             return finish_launch("fusion_sequence: n_map update");
     }
     return 0;
+}
+
+int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, const float *poses, int L, int H, int W,
+                        float sigma, float dist_th, float dot_th,
+                        float *map_points, float *map_normals, float *map_colors, float *map_ccount,
+                        long long *n_map, long long n_upper, long long capacity,
+                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    E2E_REQUIRE(depth && rgb && K && poses && map_points && map_normals && map_colors && map_ccount && n_map && workspace,
+                "fusion_sequence: null argument");
+    E2E_REQUIRE(L >= 0 && H > 0 && W > 0 && n_upper >= 0, "fusion_sequence: bad sizes");
+    E2E_REQUIRE(capacity >= n_upper + (long long)L * H * W, "fusion_sequence: capacity must be >= n_upper + L*H*W");
+    E2E_REQUIRE(workspace_bytes >= e2e_fusion_sequence_workspace_bytes(H, W, capacity), "fusion_sequence: workspace too small");
+    E2E_REQUIRE(sigma != 0.0f, "sigma must be non-zero");
+    E2E_REQUIRE((long long)H * W < (1ll << 31), "fusion_sequence: image too large");
+    if (L == 0) return 0;
+    const size_t hw = (size_t)H * W;
+    // E2E_FUSION_SEQUENCE=loop forces the per-frame launches (A/B timing, debugging)
+    static const bool force_loop = [] { const char *e = getenv("E2E_FUSION_SEQUENCE"); return e && e[0] == 'l'; }();
+    const int grid = force_loop ? 0 : sequence_grid();
+    const long long chunk = grid ? ((long long)hw + grid - 1) / grid : 0;
+    const bool coop = grid > 0 && grid <= 2048 && (chunk + SEQ_NT - 1) / SEQ_NT <= SEQ_MAX_ITERS && capacity < 0xffffffffll;
+    if (!coop)
+        return fusion_sequence_loop(depth, rgb, K, poses, L, H, W, sigma, dist_th, dot_th, map_points, map_normals, map_colors,
+                                    map_ccount, n_map, n_upper, capacity, workspace, stream);
+    SeqParams p;
+    p.depth = depth; p.rgb = rgb; p.K = K; p.poses = poses; p.L = L; p.H = H; p.W = W;
+    p.two_sigma2 = 2.0f * sigma * sigma;
+    p.ac = AssocConst{H, W, dist_th, dot_th, (float)((double)W - 0.999), (float)((double)H - 0.999)};
+    p.pts = map_points; p.nrm = map_normals; p.col = map_colors; p.cc = map_ccount; p.n_map = n_map; p.capacity = capacity;
+    unsigned char *w = (unsigned char *)workspace;
+    p.pts4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
+    p.nrm4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
+    p.col4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
+    for (int b = 0; b < 2; b++) {
+        p.vg4[b] = (float4 *)w;                     w += align256(hw * 16);
+        p.ng4[b] = (float4 *)w;                     w += align256(hw * 16);
+        p.keys[b] = (Key128 *)w;                    w += align256(hw * 16);
+    }
+    p.counts = (unsigned long long *)w;             w += align256(8 * 4096);
+    p.barrier = (unsigned *)w;
+    cudaStream_t st = (cudaStream_t)stream;
+    // frame tags of the counts start at 1, the barrier counts arrivals from 0
+    if (cudaMemsetAsync(p.counts, 0, align256(8 * 4096) + 256, st) != cudaSuccess) return finish_launch("fusion_sequence: memset");
+    void *args[] = {(void *)&p};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)fusion_sequence_kernel, dim3(grid), dim3(SEQ_NT), args, 0, st);
+    if (e != cudaSuccess) {
+        set_error("fusion_sequence: cooperative launch failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return (int)e;
+    }
+    count_launch();
+    return finish_launch("fusion_sequence");
 }
 
 }  // extern "C"
