@@ -255,13 +255,32 @@ def run_ours(args):
     host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in d.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    n_chunks = max(1, min(args.e2e_chunks, P))
+    while P % n_chunks:
+        n_chunks -= 1
+    cs = P // n_chunks
+
     def e2e_step():
-        dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        depth = dd["depth"].requires_grad_(True)
-        colors = dd["colors"].requires_grad_(True)       # gradient to the source image, as in `value`
-        T = dd["T"].requires_grad_(True)                 # gradient to the pose
-        s, t_ = colors[:, 0].permute(0, 3, 1, 2), colors[:, 1].permute(0, 3, 1, 2)
-        l = e2e.warp_photometric_loss(depth, dd["inv_K"], dd["K"], T, s, t_, "border", True)
+        """Host tensors in, loss out, through the autograd API.  The batch goes over in `n_chunks` pinned H2D copies on a
+        copy stream; chunk k's loss + gradients are computed (one sweep, in forward) while chunk k+1 is still on the wire."""
+        cur = torch.cuda.current_stream(dev)
+        losses = []
+        for k in range(n_chunks):
+            sl = slice(k * cs, (k + 1) * cs)
+            with torch.cuda.stream(copy_stream):
+                dd = {name: v[sl].to(dev, non_blocking=True) for name, v in host.items()}
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            cur.wait_event(ready)
+            for t in dd.values():
+                t.record_stream(cur)
+            depth = dd["depth"].requires_grad_(True)
+            s_ = dd["colors"][:, 0].permute(0, 3, 1, 2).detach().requires_grad_(True)   # gradient to the source image, as in `value`
+            t_ = dd["colors"][:, 1].permute(0, 3, 1, 2)
+            T = dd["T"].requires_grad_(True)                                           # gradient to the pose
+            losses.append(e2e.warp_photometric_loss(depth, dd["inv_K"], dd["K"], T, s_, t_, "border", True))
+        l = torch.stack(losses).mean()
         l.backward()
         return float(l.item())                           # 4-byte D2H read of the result
 
@@ -331,7 +350,7 @@ def run_ours(args):
                    "collective": None if world == 1 else f"NCCL all-reduce of {GRAD_BUCKET_ELEMS} fp32 depth-net gradients per step, overlapped"},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
-                "steps": e2e_steps, "loss": lval},
+                "steps": e2e_steps, "loss": lval, "h2d_chunks": n_chunks},
         "gpu_launches": launches,
         "roofline": roof, "two_kernel_path": roof_two,
         "cpu_baseline": cpu, "fusion": fusion, "loss": float(loss),
@@ -349,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=256)
     ap.add_argument("--cpu-pairs", type=int, default=16)
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-fusion", action="store_true")
     args = ap.parse_args()

@@ -70,7 +70,7 @@ def exported_symbols():
 def lib():
     global _lib
     if _lib is None:
-        path = os.path.abspath(LIB_PATH)
+        path = os.path.abspath(os.environ.get("E2E_LIB_PATH") or LIB_PATH)      # override: kernel-tuning experiments only
         if not os.path.exists(path):
             raise E2ELibraryError(
                 f"{path} not found: build it with `python end-to-end-self-supervised-slam_b200/build.py` "
