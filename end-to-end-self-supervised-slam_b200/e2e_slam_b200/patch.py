@@ -27,7 +27,7 @@ import types
 
 import torch
 
-from . import losses, ops, slam, view_synthesis
+from . import losses, odometry, ops, slam, view_synthesis
 
 
 def _module(name, **attrs):
@@ -65,14 +65,20 @@ def install(grid_sample=False, keep_real_gradslam_datasets=True):
     fusionutils = _module("gradslam.slam.fusionutils", find_active_map_points=_find_active_map_points)
     gs_slam = _module("gradslam.slam", PointFusion=slam.PointFusion, ICPSLAM=slam.ICPSLAM, fusionutils=fusionutils)
     geomutils = _module("gradslam.geometry.geometryutils", transform_pointcloud=slam.transform_pointcloud)
-    geometry = _module("gradslam.geometry", geometryutils=geomutils)
+    se3utils = _module("gradslam.geometry.se3utils", se3_exp=odometry.se3_exp)
+    geometry = _module("gradslam.geometry", geometryutils=geomutils, se3utils=se3utils)
+    icputils = _module("gradslam.odometry.icputils", point_to_plane_ICP=odometry.point_to_plane_ICP,
+                       point_to_plane_gradICP=odometry.point_to_plane_gradICP, gauss_newton_solve=odometry.gauss_newton_solve,
+                       solve_linear_system=odometry.solve_linear_system)
+    gs_odometry = _module("gradslam.odometry", icputils=icputils)
     structures = _module("gradslam.structures", Pointclouds=slam.Pointclouds, RGBDImages=slam.RGBDImages)
     datasets = real_datasets or _module("gradslam.datasets", ICL=_no_dataset, TUM=_no_dataset)
     gs = _module("gradslam", Pointclouds=slam.Pointclouds, RGBDImages=slam.RGBDImages, slam=gs_slam, geometry=geometry,
-                 structures=structures, datasets=datasets)
+                 structures=structures, datasets=datasets, odometry=gs_odometry)
     gs.__path__ = []
     sm.update({"gradslam": gs, "gradslam.slam": gs_slam, "gradslam.slam.fusionutils": fusionutils, "gradslam.geometry": geometry,
-               "gradslam.geometry.geometryutils": geomutils, "gradslam.structures": structures, "gradslam.datasets": datasets})
+               "gradslam.geometry.geometryutils": geomutils, "gradslam.geometry.se3utils": se3utils, "gradslam.odometry": gs_odometry,
+               "gradslam.odometry.icputils": icputils, "gradslam.structures": structures, "gradslam.datasets": datasets})
     # --- chamferdist ----------------------------------------------------------------------------------
     chamfer = _module("chamferdist.chamfer", knn_points=losses.knn_points)
     cd = _module("chamferdist", ChamferDistance=losses.ChamferDistance, chamfer=chamfer)

@@ -12,8 +12,9 @@ The map size lives on the device; a step launches 7 kernels and never synchronis
 Reading `points_list` does (it has to know N).
 
 Odometry: PointFusion.step localises with the frame's own pose when `odom == "gt"` or `prev_frame is None`
--- exactly gradslam's rule.  ICP / GradICP odometry is not part of this
-round; asking for it raises NotImplementedError instead of silently using another pose.
+-- exactly gradslam's rule.  Otherwise (`odom` "icp" / "gradicp") the live frame, thinned
+to every dsratio-th pixel and placed with the previous pose, is aligned to the active map points seen from the previous
+frame (odometry.point_to_plane_ICP / point_to_plane_gradICP) and the result is composed with the previous pose.
 """
 import ctypes
 import math
@@ -291,18 +292,55 @@ class PointFusion:
             raise ValueError("dist_th must be non-negative and angle_th within [0, 90]")
         self.odom, self.dist_th, self.angle_th, self.sigma = odom, float(dist_th), float(angle_th), float(sigma)
         self.dot_th = math.cos(angle_th * math.pi / 180.0)
-        self.numiters, self.dsratio = numiters, dsratio
+        self.numiters, self.dsratio, self.damp, self.dist_thresh = int(numiters), int(dsratio), float(damp), dist_thresh
+        self.lambda_max, self.B, self.B2, self.nu = float(lambda_max), float(B), float(B2), float(nu)
         self.device = torch.device(device) if device is not None else torch.device("cuda")
         self.last_association = None      # index_map / append_slot of the most recent step (tests, debugging)
 
-    def _localize(self, live_frame, prev_frame):
+    def _localize(self, pointclouds, live_frame, prev_frame):
         if self.odom == "gt" or prev_frame is None:
             if live_frame.poses is None:
                 raise ValueError("live_frame.poses must be set when odom == 'gt' or prev_frame is None")
             return live_frame.poses
-        raise NotImplementedError(
-            f"odom={self.odom!r} (ICP / GradICP odometry) is not implemented in this round (SURVEY.md section 8(f)); "
-            "construct PointFusion(odom='gt') -- the reference's own GT_SLAM (train_depth.py:118) -- or pass prev_frame=None")
+        from . import odometry
+        if not isinstance(prev_frame, RGBDImages):
+            raise TypeError(f"Expected prev_frame to be of type RGBDImages. Got {type(prev_frame)}.")
+        if prev_frame.poses is None:
+            raise ValueError("prev_frame.poses must be set for ICP odometry")
+        B, _, H, W = live_frame.shape
+        if len(pointclouds) != B or not pointclouds.has_points:
+            raise ValueError("ICP odometry needs a non-empty map (fuse the first frame with prev_frame=None)")
+        ds = self.dsratio
+        poses = []
+        for b in range(B):
+            prev_pose = f32(prev_frame.poses[b, 0], "poses").detach().contiguous()
+            depth = f32(live_frame.depth_image[b, 0, :, :, 0], "depth_image")
+            K = f32(live_frame.intrinsics[b, 0], "intrinsics").contiguous()
+            if torch.is_grad_enabled() and depth.requires_grad:       # differentiable vertex map (GradICP's purpose)
+                us = torch.arange(W, dtype=torch.float32, device=depth.device)[None, :]
+                vs = torch.arange(H, dtype=torch.float32, device=depth.device)[:, None]
+                V = torch.stack([(us - K[0, 2]) / K[0, 0] * depth, (vs - K[1, 2]) / K[1, 1] * depth, depth], -1)
+                vg, valid = V @ prev_pose[:3, :3].t() + prev_pose[:3, 3], depth > 0
+            else:
+                with torch.cuda.device(depth.device):
+                    vg, _, _, valid = _frame_maps(depth.contiguous(), K, prev_pose, self.sigma)
+                valid = valid.bool()
+            live_pts = vg[::ds, ::ds][valid[::ds, ::ds]]
+            m = pointclouds._maps[b]
+            n = m.count()
+            inside, h, w = odometry.active_map_points(m.pts[:n].detach(), K, prev_pose, H, W)
+            keep = inside & (h % ds == 0) & (w % ds == 0)
+            tgt, nrm = m.pts[:n].detach()[keep], m.nrm[:n].detach()[keep]
+            if live_pts.shape[0] < 6 or tgt.shape[0] < 6:
+                raise RuntimeError(f"ICP odometry: too few points (live {live_pts.shape[0]}, active map {tgt.shape[0]})")
+            eye = torch.eye(4, dtype=torch.float32, device=depth.device)
+            if self.odom == "icp":
+                T, _ = odometry.point_to_plane_ICP(live_pts[None], tgt[None], nrm[None], eye, self.numiters, self.damp, self.dist_thresh)
+            else:
+                T, _ = odometry.point_to_plane_gradICP(live_pts[None], tgt[None], nrm[None], eye, self.numiters, self.damp,
+                                                       self.dist_thresh, self.lambda_max, self.B, self.B2, self.nu)
+            poses.append(T @ prev_pose)
+        return torch.stack(poses).unsqueeze(1)
 
     def step(self, pointclouds, live_frame, prev_frame=None, inplace=False):
         if not isinstance(pointclouds, Pointclouds):
@@ -311,7 +349,7 @@ class PointFusion:
             raise TypeError(f"Expected live_frame to be of type RGBDImages. Got {type(live_frame)}.")
         if live_frame.shape[1] != 1:
             raise ValueError(f"live_frame must have sequence length 1. Got {live_frame.shape[1]}.")
-        poses = self._localize(live_frame, prev_frame)
+        poses = self._localize(pointclouds, live_frame, prev_frame)
         live_frame.poses = poses
         B, _, H, W = live_frame.shape
         if len(pointclouds) not in (0, B):

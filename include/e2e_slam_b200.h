@@ -246,6 +246,23 @@ int e2e_knn1_fwd(const float *query, const float *transform, const float *ref, l
 int e2e_knn1_bwd(const float *query, const float *transform, const float *ref, long long P1, long long P2,
                  const long long *idx, const float *grad_dist2, float *grad_query, float *grad_ref, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Point-to-plane ICP / GradICP odometry (gradslam PointFusion with odom = "icp" / "gradicp", the reference's shipped
+ * default: configs/config.yaml:30-34; constructed at train_depth.py:111-116, stepped at online_adaption.py:362-363,
+ * train_depth.py:378-381).  Replaces gradslam.odometry.icputils.point_to_plane_ICP / point_to_plane_gradICP (kNN through
+ * chamferdist, Jacobian / normal equations / solve as ~40 torch launches and two host syncs per iteration).
+ * src [N,3], tgt / tgt_normals [M,3], T_init / T_out device 4x4 row-major.  The iteration loop runs without host
+ * synchronisation (state on the device).  dist_thresh < 0: keep every pair; otherwise pairs with SQUARED distance below
+ * it.  grad_icp = 0: Gauss-Newton with fixed damping `damp`; 1: logistic-gated Levenberg-Marquardt (lambda_max, B, B2,
+ * nu; conventions in oracle/icp_oracle.py).  idx_out (nullable) [N] int64: correspondences of the last linearisation;
+ * errs (nullable) [numiters] fp32: |b|^2 before every step.
+ * --------------------------------------------------------------------------------------------- */
+size_t e2e_icp_workspace_bytes(long long N);
+int e2e_icp_point_to_plane(const float *src, long long N, const float *tgt, const float *tgt_normals, long long M,
+                           const float *T_init, int numiters, float damp, float dist_thresh,
+                           int grad_icp, float lambda_max, float B, float B2, float nu,
+                           float *T_out, long long *idx_out, float *errs, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,7 +215,7 @@ def test_pointfusion_interface_errors():
         PointFusion(odom="gt").step([], rgbd[:, 0])
     with pytest.raises(ValueError):
         PointFusion(odom="gt").step(Pointclouds(device="cuda"), rgbd)             # sequence length 2
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                                               # ICP odometry against an empty map
         PointFusion(odom="gradicp", device="cuda").step(Pointclouds(device="cuda"), rgbd[:, 1], rgbd[:, 0])
     pc, p = PointFusion(odom="gradicp", device="cuda").step(Pointclouds(device="cuda"), rgbd[:, 0], prev_frame=None)
     assert pc.has_points and p.shape == (1, 1, 4, 4)
