@@ -22,6 +22,8 @@
 // the VALUES it stores (each must be 0 or have 2^-40 <= |v| <= 2^40, which bounds every window sum and
 // product away from the failing range) and the CTA votes once; a CTA that sees anything else (denormal
 // garbage, inf, NaN) takes the IEEE-division code path.  Either way the result is the reference's bits.
+#include <cstdlib>
+
 #include "warp_photo_common.cuh"
 
 namespace e2e {
@@ -449,8 +451,9 @@ extern "C" {
 
 size_t e2e_warp_photo_workspace_bytes(int B, int H, int W)
 {
-    // forward: one float per CTA; backward: 12 floats per CTA.  256-byte slack for alignment.
-    return partial_count(B, H, W) * 12 * sizeof(float) + 256;
+    // forward: one float per CTA; backward: the streaming kernel's partials (or 12 floats per CTA of the tile kernel)
+    const size_t tile = partial_count(B, H, W) * 12 * sizeof(float) + 256, stream = stream_workspace_bytes(B, H, W);
+    return tile > stream ? tile : stream;
 }
 
 int e2e_warp_photo_fwd(const float *depth, const float *inv_K, const float *K, const float *T,
@@ -506,6 +509,11 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
         const ImgView gv{grad_src, p.g_src.sb, p.g_src.sc, p.g_src.sh, p.g_src.sw};
         E2E_REQUIRE(view_fits_int32(gv, 3, H, W), "grad_src strides do not fit 32-bit in-image offsets");
     }
+    // Default: the streaming kernel (csrc/warp_photo_fused.cu) with the upstream gradient read per pixel -- it re-derives the
+    // forward quantities in the same sweep, half the time of the tile kernel below.  E2E_BWD_TILE=1 selects the tile kernel.
+    static const bool use_tile = [] { const char *e = getenv("E2E_BWD_TILE"); return e && e[0] == '1'; }();
+    if (!use_tile && H <= 8189 && W <= 8189)
+        return launch_stream(p, B, H, W, nullptr, grad_P, workspace, workspace_bytes, st);
     const dim3 grid = tile_grid(B, H, W, B_TH, B_TW);
     const size_t nct = (size_t)grid.x * grid.y * grid.z;
     if (grad_P) {
