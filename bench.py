@@ -330,6 +330,27 @@ def run_ours(args):
                "sample": f"{args.cpu_pairs} of the 256 pairs, 480x640, fwd+bwd, torch-op restatement of the reference "
                          f"(oracle/torch_oracle.py), best of 3 after 1 warm-up, {threads} threads"}
 
+    # ---- secondary: one key-frame pair (config C1 shape) -- launch-latency bound, reported as latency ------------
+    single = None
+    if world == 1:
+        p1 = ops.WarpPhotoPlan(1, H, W, dev)
+        a1 = tuple(t[:1] for t in (d["depth"], d["inv_K"], d["K"], d["T"])) + (src[:1], tgt[:1])
+        l0 = ops.launch_count()
+        eager_ms = timed(lambda: p1.value_and_grad(*a1), n=50)
+        per_call = (ops.launch_count() - l0) // 51
+        graph_ms = None
+        try:                                            # the same call captured once and replayed as a CUDA graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                p1.value_and_grad(*a1)
+            graph_ms = timed(g.replay, n=200)
+        except Exception as e:                          # capture is an optimisation, not part of the contract
+            graph_ms = None
+            sys.stderr.write(f"single-pair graph capture failed: {e}\n")
+        single = {"workload": "C1 single ICL-shaped 480x640 pair, loss + gradients to depth / source / pose", "eager_us": eager_ms * 1e3,
+                  "cuda_graph_us": None if graph_ms is None else graph_ms * 1e3, "launches_per_call": per_call,
+                  "px_per_s_graph": None if graph_ms is None else H * W / (graph_ms * 1e-3)}
+
     # ---- secondary metric: PointFusion points fused/s (config C3) ----------------------------------------
     fusion = None
     if world == 1 and not args.skip_fusion:
@@ -353,7 +374,7 @@ def run_ours(args):
                 "steps": e2e_steps, "loss": lval, "h2d_chunks": n_chunks},
         "gpu_launches": launches,
         "roofline": roof, "two_kernel_path": roof_two,
-        "cpu_baseline": cpu, "fusion": fusion, "loss": float(loss),
+        "cpu_baseline": cpu, "fusion": fusion, "single_pair": single, "loss": float(loss),
     }
     print(json.dumps(out))
     if world > 1:
