@@ -1,6 +1,8 @@
 """GPU parity tests of PointFusion (vertex/normal/confidence maps, association index map, merge + append)
 and of the K = 1 nearest-neighbour kernels, against oracle/fusion_oracle.py (numpy; gradslam / chamferdist
 semantics as frozen there -- parity unpinned, see its header).  Integer outputs must be BIT-EXACT."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -301,3 +303,41 @@ def test_point_supervision_full_size():
     ours_i, ours_d = out.idx[0, :, 0].cpu().numpy(), out.dists[0, :, 0].cpu().numpy()
     assert (ours_i == i).mean() > 0.9999
     assert np.abs(ours_d - d ** 2).max() <= 1e-5 * (d ** 2).max()
+
+
+@pytest.mark.parametrize("H,W", [(16, 20), (120, 160), (270, 480)])
+def test_sequence_entry_continues_an_existing_map(H, W):
+    """e2e_fusion_sequence on frames 0..5 in one call == frames 0..2, then a second call that starts from that map
+    (the kernel's prologue converts the caller's [n,3] arrays to its working records): every array bit for bit.
+    Sizes: a frame smaller than one CTA's share, the usual quarter frame, and one with several sub-blocks per CTA."""
+    import ctypes
+    from e2e_slam_b200._lib import check, lib, ptr, stream_ptr
+    from e2e_slam_b200.synthetic import room_sequence
+    L = 6
+    depth, rgb, K, poses = room_sequence(L, H, W, device="cuda")
+    depth[:, H // 4:H // 3, W // 3:W // 2] = 0.0
+
+    def run(frames, state=None):
+        cap = L * H * W
+        z = dict(dtype=torch.float32, device="cuda")
+        if state is None:
+            pts, nrm, col, cc = torch.zeros(cap, 3, **z), torch.zeros(cap, 3, **z), torch.zeros(cap, 3, **z), torch.zeros(cap, **z)
+            n, upper = torch.zeros(2, dtype=torch.int64, device="cuda"), 0
+        else:
+            pts, nrm, col, cc, n = state
+            upper = int(n[0])
+        nws = lib().e2e_fusion_sequence_workspace_bytes(H, W, cap)
+        ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+        d, c, p = depth[frames].contiguous(), rgb[frames].contiguous(), poses[frames].contiguous()
+        check(lib().e2e_fusion_sequence(ptr(d), ptr(c), ptr(K), ptr(p), d.shape[0], H, W, ctypes.c_float(0.6), ctypes.c_float(0.05),
+                                        ctypes.c_float(math.cos(math.radians(20))), ptr(pts), ptr(nrm), ptr(col), ptr(cc), ptr(n),
+                                        upper, cap, ptr(ws), nws, stream_ptr()), "e2e_fusion_sequence")
+        torch.cuda.synchronize()
+        return pts, nrm, col, cc, n
+
+    whole = run(slice(0, 6))
+    part = run(slice(3, 6), run(slice(0, 3)))
+    n = int(whole[4][0])
+    assert n == int(part[4][0]) and n > (depth[0] > 0).sum()
+    for a, b in zip(whole[:4], part[:4]):
+        assert torch.equal(a[:n], b[:n])
