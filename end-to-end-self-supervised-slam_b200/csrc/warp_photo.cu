@@ -123,9 +123,10 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float *part
 }
 
 // grad_P[b][e] = sum over the CTAs of batch element b of partial[cta][e]  (fixed order -> deterministic)
-__global__ void __launch_bounds__(256) reduce_gP_kernel(const float *partial, int ctas_per_b, float *gP)
+__global__ void __launch_bounds__(256) reduce_gP_kernel(const float *partial, int ctas_per_b, float *gP, const float *skip_flag)
 {
     __shared__ double sh[8];
+    if (skip_flag && __ldg(skip_flag) != 0.0f) return;      // conditional backward: the partials were not produced
     const int b = blockIdx.x / 12, e = blockIdx.x % 12;
     double acc = 0.0;
     for (int i = threadIdx.x; i < ctas_per_b; i += blockDim.x) acc += (double)partial[((long long)b * ctas_per_b + i) * 12 + e];
@@ -146,9 +147,9 @@ int launch_reduce_partials(const float *partial, long long n, double scale, floa
     return finish_launch("reduce_partials_kernel");
 }
 
-int launch_reduce_gP(const float *partial, int ctas_per_b, int B, float *gP, cudaStream_t st)
+int launch_reduce_gP(const float *partial, int ctas_per_b, int B, float *gP, cudaStream_t st, const float *skip_flag)
 {
-    reduce_gP_kernel<<<B * 12, 256, 0, st>>>(partial, ctas_per_b, gP);
+    reduce_gP_kernel<<<B * 12, 256, 0, st>>>(partial, ctas_per_b, gP, skip_flag);
     count_launch();
     return finish_launch("reduce_gP_kernel");
 }
@@ -495,6 +496,18 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
                        float *grad_depth, float *grad_src, const int64_t grad_src_strides[4], float *grad_P,
                        void *workspace, size_t workspace_bytes, void *stream)
 {
+    return e2e_warp_photo_bwd_cond(depth, inv_K, K, T, src, src_strides, tgt, tgt_strides, B, H, W, padding_mode, use_mask, eps,
+                                   grad_loss_map, grad_scalar, scalar_scale, nullptr, grad_depth, grad_src, grad_src_strides, grad_P,
+                                   workspace, workspace_bytes, stream);
+}
+
+int e2e_warp_photo_bwd_cond(const float *depth, const float *inv_K, const float *K, const float *T,
+                            const float *src, const int64_t src_strides[4], const float *tgt, const int64_t tgt_strides[4],
+                            int B, int H, int W, int padding_mode, int use_mask, float eps,
+                            const float *grad_loss_map, const float *grad_scalar, float scalar_scale, const float *skip_if_nonzero,
+                            float *grad_depth, float *grad_src, const int64_t grad_src_strides[4], float *grad_P,
+                            void *workspace, size_t workspace_bytes, void *stream)
+{
     cudaStream_t st = (cudaStream_t)stream;
     WPParams p = {};
     E2E_REQUIRE(depth && inv_K && K && T && src && tgt && grad_depth, "null pointer");
@@ -502,6 +515,8 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
     p.depth = depth; p.inv_K = inv_K; p.K = K; p.T = T;
     if (int rc = set_views(p, src, src_strides, tgt, tgt_strides, 3)) return rc;
     p.g_loss_map = grad_loss_map; p.g_scalar = grad_scalar; p.g_scale = scalar_scale;
+    p.skip_flag = skip_if_nonzero;
+    E2E_REQUIRE(!skip_if_nonzero || grad_loss_map, "the conditional backward takes the upstream gradient as a map");
     p.g_depth = grad_depth;
     if (grad_src) {
         E2E_REQUIRE(grad_src_strides, "grad_src needs strides");
@@ -512,8 +527,9 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
     // Default: the streaming kernel (csrc/warp_photo_fused.cu) with the upstream gradient read per pixel -- it re-derives the
     // forward quantities in the same sweep, half the time of the tile kernel below.  E2E_BWD_TILE=1 selects the tile kernel.
     static const bool use_tile = [] { const char *e = getenv("E2E_BWD_TILE"); return e && e[0] == '1'; }();
-    if (!use_tile && H <= 8189 && W <= 8189)
+    if ((!use_tile || skip_if_nonzero) && H <= 8189 && W <= 8189)
         return launch_stream(p, B, H, W, nullptr, grad_P, workspace, workspace_bytes, st);
+    E2E_REQUIRE(!skip_if_nonzero, "the conditional backward needs H, W <= 8189");
     const dim3 grid = tile_grid(B, H, W, B_TH, B_TW);
     const size_t nct = (size_t)grid.x * grid.y * grid.z;
     if (grad_P) {
@@ -523,7 +539,7 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
     const bool il = (p.src.sc == 1 && p.tgt.sc == 1);
     if (int rc = il ? launch_bwd<MODE_WARP, 3, false, true>(p, grid, st) : launch_bwd<MODE_WARP, 3, false, false>(p, grid, st)) return rc;
     if (grad_P) {
-        reduce_gP_kernel<<<B * 12, 256, 0, st>>>(p.gP_partial, (int)(grid.x * grid.y), grad_P);
+        reduce_gP_kernel<<<B * 12, 256, 0, st>>>(p.gP_partial, (int)(grid.x * grid.y), grad_P, nullptr);
         count_launch();
         if (int rc = finish_launch("reduce_gP_kernel")) return rc;
     }

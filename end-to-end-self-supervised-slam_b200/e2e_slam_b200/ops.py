@@ -7,6 +7,7 @@
 backward kernel.  Everything is fp32; all tensors must live on a CUDA device.
 """
 import ctypes
+import os
 
 import torch
 
@@ -40,9 +41,19 @@ def _workspace(B, H, W, device):
     return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
+_SPECULATE = os.environ.get("E2E_SPECULATE", "1") != "0"
+
+
 class _WarpPhotometric(torch.autograd.Function):
     """mode 'map'  -> returns loss_map [B,1,H,W] (+ syn, valid, pix when materialise=True)
-       mode 'mean' -> returns the scalar mean of the loss map (lean path, nothing else is written)"""
+       mode 'mean' -> returns the scalar mean of the loss map (lean path, nothing else is written)
+
+    Map mode with autograd: the reference reduces the map with `.mean(1, keepdim=True).mean()` (train_depth.py:629, 657), so
+    the gradient that comes back is the same number at every pixel.  forward() therefore runs the single-sweep kernel
+    (e2e_warp_photo_vg_map), which writes the map AND the gradients for that uniform case; backward() checks the upstream
+    map on the device (e2e_upstream_uniform), rescales the stored gradients, and enqueues the streaming backward kernel
+    with a skip flag -- it only does work when the upstream gradient is not uniform (min-reprojection, weighting).  No host
+    synchronisation either way.  E2E_SPECULATE=0 restores forward kernel + unconditional backward kernel."""
 
     @staticmethod
     def forward(ctx, depth, inv_K, K, T, src, tgt, padding_mode, use_mask, eps, mode, materialise):
@@ -59,6 +70,32 @@ class _WarpPhotometric(torch.autograd.Function):
         pad = _pad_code(padding_mode)
         ws, ws_bytes = _workspace(B, H, W, dev)
         syn = valid = pix = loss_map = loss_mean = None
+        need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
+        ctx.spec = None
+        if mode == "map" and _SPECULATE and (need_depth or need_K or need_T or need_src):
+            loss_map = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+            if materialise:
+                syn = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+                valid = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+                pix = torch.empty(B, H, W, 2, dtype=torch.float32, device=dev)
+            grad_depth = torch.empty_like(depth_c)
+            grad_src = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
+            grad_P = torch.empty(B, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
+            with torch.cuda.device(dev):
+                rc = lib().e2e_warp_photo_vg_map(ptr(depth_c), ptr(inv_K_c), ptr(K_c), ptr(T_c), ptr(src), strides4(src),
+                                                 ptr(tgt), strides4(tgt), B, H, W, pad, int(bool(use_mask)), ctypes.c_float(eps),
+                                                 ptr(loss_map), ptr(syn), ptr(valid), ptr(pix), None,
+                                                 ptr(grad_depth), ptr(grad_src),
+                                                 strides4(grad_src) if grad_src is not None else None,
+                                                 ptr(grad_P), ptr(ws), ws_bytes, stream_ptr())
+            check(rc, "e2e_warp_photo_vg_map")
+            ctx.spec = (grad_depth, grad_src, grad_P)
+            ctx.save_for_backward(depth_c, inv_K_c, K_c, T_c, src, tgt)
+            ctx.cfg = (B, H, W, pad, int(bool(use_mask)), float(eps), mode)
+            if materialise:
+                ctx.mark_non_differentiable(syn, valid, pix)
+                return loss_map, syn, valid, pix
+            return loss_map
         if mode == "map":
             loss_map = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
             if materialise:
@@ -90,10 +127,29 @@ class _WarpPhotometric(torch.autograd.Function):
         g = grads[0]
         dev = depth.device
         need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
+        ws, ws_bytes = _workspace(B, H, W, dev)
+        if ctx.spec is not None:                      # gradients for a uniform upstream gradient were produced by forward()
+            grad_depth, grad_src, grad_P = ctx.spec
+            ctx.spec = None
+            g_map = f32(g, "grad").contiguous()
+            scale2 = torch.empty(2, dtype=torch.float32, device=dev)
+            n = B * H * W
+            with torch.cuda.device(dev):
+                check(lib().e2e_upstream_uniform(ptr(g_map), n, float(n), ptr(scale2), stream_ptr()), "e2e_upstream_uniform")
+                check(lib().e2e_scale_or_zero(ptr(grad_depth), grad_depth.numel(), ptr(grad_src),
+                                              grad_src.numel() if grad_src is not None else 0, ptr(grad_P),
+                                              grad_P.numel() if grad_P is not None else 0, ptr(scale2), stream_ptr()),
+                      "e2e_scale_or_zero")
+                rc = lib().e2e_warp_photo_bwd_cond(ptr(depth), ptr(inv_K), ptr(K), ptr(T), ptr(src), strides4(src), ptr(tgt),
+                                                   strides4(tgt), B, H, W, pad, use_mask, ctypes.c_float(eps), ptr(g_map), None,
+                                                   ctypes.c_float(1.0), ptr(scale2[1:]), ptr(grad_depth), ptr(grad_src),
+                                                   strides4(grad_src) if grad_src is not None else None,
+                                                   ptr(grad_P), ptr(ws), ws_bytes, stream_ptr())
+            check(rc, "e2e_warp_photo_bwd_cond")
+            return _WarpPhotometric._finish(ctx, K, T, grad_depth, grad_src, grad_P)
         grad_depth = torch.empty_like(depth)
         grad_src = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
         grad_P = torch.empty(B, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
-        ws, ws_bytes = _workspace(B, H, W, dev)
         if mode == "map":
             g_map, g_scalar, scale = f32(g, "grad").contiguous(), None, 1.0
         else:
@@ -107,6 +163,11 @@ class _WarpPhotometric(torch.autograd.Function):
                                           strides4(grad_src) if grad_src is not None else None,
                                           ptr(grad_P), ptr(ws), ws_bytes, stream_ptr())
         check(rc, "e2e_warp_photo_bwd")
+        return _WarpPhotometric._finish(ctx, K, T, grad_depth, grad_src, grad_P)
+
+    @staticmethod
+    def _finish(ctx, K, T, grad_depth, grad_src, grad_P):
+        need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
         grad_K = grad_T = None
         if grad_P is not None:
             # P = (K @ T)[:3]  =>  dL/dT = K[:3]^T dL/dP ,  dL/dK[:3] = dL/dP T^T   (4x4 host-side plumbing)

@@ -78,6 +78,17 @@ int e2e_warp_photo_bwd(const float *depth, const float *inv_K, const float *K, c
                        float *grad_depth, float *grad_src, const int64_t grad_src_strides[4], float *grad_P,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* Conditional form of e2e_warp_photo_bwd for callers that already hold gradients computed for a UNIFORM upstream gradient
+ * (e2e_warp_photo_vg_map below): when the device-resident float *skip_if_nonzero is non-zero the kernels return at once.
+ * grad_loss_map is required. */
+int e2e_warp_photo_bwd_cond(const float *depth, const float *inv_K, const float *K, const float *T,
+                            const float *src, const int64_t src_strides[4],
+                            const float *tgt, const int64_t tgt_strides[4],
+                            int B, int H, int W, int padding_mode, int use_mask, float eps,
+                            const float *grad_loss_map, const float *grad_scalar, float scalar_scale, const float *skip_if_nonzero,
+                            float *grad_depth, float *grad_src, const int64_t grad_src_strides[4], float *grad_P,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* Single-pass value + gradient of the SCALAR loss  mean_{B,H,W} photometric_loss(...)  (the reference's use:
  * `losses += photometric.mean()` train_depth.py:657 followed by `loss.backward()` :307): one sweep over the
  * inputs produces loss_mean [1] and d loss_mean / d {depth, source image, P = (K@T)[:3]} for an upstream
@@ -93,6 +104,23 @@ int e2e_warp_photo_vg(const float *depth, const float *inv_K, const float *K, co
                       int B, int H, int W, int padding_mode, int use_mask, float eps,
                       float *loss_mean, float *grad_depth, float *grad_src, const int64_t grad_src_strides[4],
                       float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
+
+/* The same sweep with the forward tensors the reference's scripts keep (train_depth.py:581-590, 726) as outputs: loss_map
+ * [B,1,H,W] (bit-exact, like e2e_warp_photo_fwd), syn [B,3,H,W], valid [B,1,H,W], pix [B,H,W,2]; each nullable, at least one
+ * required; loss_mean nullable.  The gradients are those of mean(loss_map), i.e. of an upstream gradient 1/(B*H*W) at every
+ * pixel -- what `photometric.mean(1, keepdim=True).mean()` (train_depth.py:629, 657) sends back.  A caller that later
+ * receives an arbitrary upstream map g checks it with e2e_upstream_uniform (scale2[0] = factor for the stored gradients, 0
+ * if g is not uniform; scale2[1] = 1 if uniform), applies e2e_scale_or_zero and runs e2e_warp_photo_bwd_cond with
+ * skip_if_nonzero = scale2 + 1: no host synchronisation, and the backward kernel only does work when g is not uniform. */
+int e2e_warp_photo_vg_map(const float *depth, const float *inv_K, const float *K, const float *T,
+                          const float *src, const int64_t src_strides[4],
+                          const float *tgt, const int64_t tgt_strides[4],
+                          int B, int H, int W, int padding_mode, int use_mask, float eps,
+                          float *loss_map, float *syn, float *valid, float *pix, float *loss_mean,
+                          float *grad_depth, float *grad_src, const int64_t grad_src_strides[4],
+                          float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
+int e2e_upstream_uniform(const float *g, long long n, double n_total, float *scale2, void *stream);
+int e2e_scale_or_zero(float *a, long long na, float *b, long long nb, float *c, long long nc, const float *scale, void *stream);
 
 int e2e_scale_by_scalar(float *a, long long na, float *b, long long nb, float *c, long long nc,
                         const float *scalar, void *stream);
