@@ -295,3 +295,40 @@ def test_photometric_standalone(e2e):
     lg.mean().backward()
     assert same_values(lg.detach().cpu().numpy(), lo.detach().numpy()) == 0
     assert rel_max(pg.grad.cpu().numpy(), po.grad.numpy()) <= RTOL
+
+
+@pytest.mark.parametrize("upstream", ["uniform", "weighted", "zero_rows"])
+def test_speculative_map_path_equals_forward_plus_backward(e2e, upstream, monkeypatch):
+    """Map mode under autograd: the forward sweep also produces the gradients for a uniform upstream gradient and the
+    backward only rescales them -- or, when the upstream map is not uniform, clears them and runs the backward kernel.
+    Either way outputs and gradients must equal the forward-kernel + backward-kernel route (ops._SPECULATE = False)."""
+    from e2e_slam_b200 import ops
+    from e2e_slam_b200.synthetic import make_pairs
+    d = make_pairs(2, 45, 70, "tum", seed=31, rot_deg=3.0, trans=0.1, holes=0.1, device="cuda")
+
+    def run(spec):
+        monkeypatch.setattr(ops, "_SPECULATE", spec)
+        depth = d["depth"].clone().requires_grad_(True)
+        src = d["colors"][:, 0].permute(0, 3, 1, 2).detach().requires_grad_(True)
+        T = d["T"].clone().requires_grad_(True)
+        lm, syn, valid, pix = e2e.warp_photometric(depth, d["inv_K"], d["K"], T, src, d["colors"][:, 1].permute(0, 3, 1, 2),
+                                                   "border", True, need_outputs=True)
+        if upstream == "uniform":
+            loss = lm.mean(1, keepdim=True).mean()                       # train_depth.py:629, 657
+        elif upstream == "weighted":
+            loss = (lm * (0.5 + valid)).mean()
+        else:
+            loss = lm[:, :, ::2].mean()                                  # zeros in every other row of the upstream map
+        loss.backward()
+        return [t.detach().clone() for t in (lm, syn, valid, pix, depth.grad, src.grad, T.grad)]
+
+    a, b = run(True), run(False)
+    for name, x, y in zip(("loss_map", "syn", "valid", "pix"), a[:4], b[:4]):
+        assert torch.equal(x, y), f"{name} differs between the two routes"
+    for name, x, y in zip(("g_depth", "g_src", "g_T"), a[4:], b[4:]):
+        # uniform: same arithmetic up to the order of the scalar factors; otherwise the very same kernel ran in both routes,
+        # and only grad_src (fp32 atomics, order not fixed) may differ in the last bits
+        if upstream != "uniform" and name != "g_src":
+            assert torch.equal(x, y), name
+        else:
+            assert rel_max(x.cpu().numpy(), y.cpu().numpy()) <= 2e-6, name
