@@ -251,6 +251,17 @@ def run_ours(args):
     fwd_avg = timed(lambda: plan.forward(*kargs))
     bwd_avg = timed(lambda: plan.backward(*kargs))
 
+    def map_step(n_pairs=64):
+        """What patch.fuse() gives the unmodified scripts: forward keeping loss map / synthesized frame / valid mask, the
+        reference's `.mean(1, keepdim=True).mean()`, backward (64 pairs: the materialised outputs of 256 would not tell more)."""
+        dp = d["depth"][:n_pairs].detach().requires_grad_(True)
+        sp = src[:n_pairs].detach().requires_grad_(True)
+        lm, syn, valid, _ = e2e.warp_photometric(dp, d["inv_K"][:n_pairs], d["K"][:n_pairs], d["T"][:n_pairs], sp, tgt[:n_pairs],
+                                                 "border", True, need_outputs=True)
+        lm.mean(1, keepdim=True).mean().backward()
+    map_pairs = min(64, P)
+    map_avg = timed(lambda: map_step(map_pairs))
+
     # ---- end to end through the public API: host inputs, pinned H2D inside the timed region ----------
     host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in d.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -319,7 +330,11 @@ def run_ours(args):
     roof_two = {"fwd_kernel_ms": fwd_avg, "bwd_kernel_ms_incl_zero_fill": bwd_avg,
                 "fwd_frac": ALG_BYTES_FWD * npx / (fwd_avg * 1e-3) / 1e9 / peak,
                 "bwd_frac": ALG_BYTES_BWD * npx / (bwd_avg * 1e-3) / 1e9 / peak,
-                "note": "separate forward (loss map) and backward (arbitrary upstream gradient) kernels, not in the timed step"}
+                "map_path_autograd_ms": map_avg, "map_path_pairs": map_pairs,
+                "map_path_px_per_s": map_pairs * H * W / (map_avg * 1e-3),
+                "note": "not in the timed step.  fwd = loss-map forward kernel (no autograd); bwd = backward for an arbitrary upstream "
+                        "gradient (streaming kernel); map_path = what patch.fuse() gives the unmodified scripts: forward keeping loss map / "
+                        "synthesized frame / valid mask + .mean(1).mean() + backward through autograd (one sweep + rescale)"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------------------------
     cpu = None
