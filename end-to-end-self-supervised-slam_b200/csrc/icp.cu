@@ -4,7 +4,7 @@
 //
 // The whole iteration loop is enqueued by ONE call and never synchronises with the host: the current transform, the
 // damping and the Gauss-Newton step live in device memory.  Per iteration
-//     knn1 (csrc/knn.cu, exact brute force)  ->  linearize (Jacobian rows + 6x6 normal equations, block partials)
+//     knn1 (csrc/knn_grid.cu: the target is gridded once per call, exact)  ->  linearize (Jacobian rows + 6x6 normal equations, block partials)
 //     ->  solve (fixed-order fp64 reduction of the partials, 6x6 solve, se3 exponential, transform update)
 //     ->  transform of the source cloud;
 // GradICP adds the look-ahead (trial transform, knn1, linearize) and the logistic gates of step and damping.
@@ -196,10 +196,10 @@ using namespace e2e;
 
 extern "C" {
 
-size_t e2e_icp_workspace_bytes(long long N)
+size_t e2e_icp_workspace_bytes(long long N, long long M)
 {
     if (N < 0) N = 0;
-    return 2 * a256((size_t)N * 12) + 2 * a256((size_t)N * 4) + 2 * a256((size_t)N * 8) + a256((size_t)kNumSMs * 4 * ICP_NV * 4) +
+    return a256(e2e_knn1_grid_workspace_bytes(M)) + 2 * a256((size_t)N * 12) + 2 * a256((size_t)N * 4) + 2 * a256((size_t)N * 8) + a256((size_t)kNumSMs * 4 * ICP_NV * 4) +
            a256(sizeof(IcpState)) + 256;
 }
 
@@ -211,9 +211,10 @@ int e2e_icp_point_to_plane(const float *src, long long N, const float *tgt, cons
     cudaStream_t s = (cudaStream_t)stream;
     E2E_REQUIRE(src && tgt && tgt_normals && T_init && T_out && workspace, "icp: null argument");
     E2E_REQUIRE(N > 0 && M > 0 && numiters >= 0, "icp: empty point cloud or negative iteration count (N=%lld, M=%lld)", N, M);
-    E2E_REQUIRE(workspace_bytes >= e2e_icp_workspace_bytes(N), "icp: workspace too small (e2e_icp_workspace_bytes)");
+    E2E_REQUIRE(workspace_bytes >= e2e_icp_workspace_bytes(N, M), "icp: workspace too small (e2e_icp_workspace_bytes)");
     E2E_REQUIRE(!grad_icp || nu != 0.0f, "icp: nu must be non-zero");
     unsigned char *w = (unsigned char *)workspace;
+    void *grid = w;                     w += a256(e2e_knn1_grid_workspace_bytes(M));      // the target cloud, gridded once
     float *cur = (float *)w;            w += a256((size_t)N * 12);
     float *trial = (float *)w;          w += a256((size_t)N * 12);
     float *dist2 = (float *)w;          w += a256((size_t)N * 4);
@@ -223,17 +224,18 @@ int e2e_icp_point_to_plane(const float *src, long long N, const float *tgt, cons
     float *partials = (float *)w;       w += a256((size_t)kNumSMs * 4 * ICP_NV * 4);
     IcpState *st = (IcpState *)w;
     const int nb = icp_blocks(N);
+    if (int rc = e2e_knn1_grid_build(tgt, M, grid, e2e_knn1_grid_workspace_bytes(M), stream)) return rc;
     icp_init_kernel<<<1, 32, 0, s>>>(st, T_init, (double)damp);
     icp_transform_kernel<<<nb, ICP_NT, 0, s>>>(src, T_init, cur, N);
     count_launch(2);
     for (int it = 0; it < numiters; it++) {
-        if (int rc = e2e_knn1_fwd(cur, nullptr, tgt, N, M, dist2, idx, stream)) return rc;
+        if (int rc = e2e_knn1_grid_query(cur, nullptr, N, M, dist2, idx, grid, stream)) return rc;
         icp_linearize_kernel<<<nb, ICP_NT, 0, s>>>(cur, tgt, tgt_normals, idx, dist2, dist_thresh, N, partials);
         icp_solve_kernel<<<1, 32, 0, s>>>(partials, nb, st, 0, grad_icp, damp, lambda_max, B, B2, nu, errs, it);
         count_launch(2);
         if (grad_icp) {
             icp_transform_kernel<<<nb, ICP_NT, 0, s>>>(cur, st->step, trial, N);
-            if (int rc = e2e_knn1_fwd(trial, nullptr, tgt, N, M, dist2_t, idx_t, stream)) return rc;
+            if (int rc = e2e_knn1_grid_query(trial, nullptr, N, M, dist2_t, idx_t, grid, stream)) return rc;
             icp_linearize_kernel<<<nb, ICP_NT, 0, s>>>(trial, tgt, tgt_normals, idx_t, dist2_t, dist_thresh, N, partials);
             icp_solve_kernel<<<1, 32, 0, s>>>(partials, nb, st, 1, grad_icp, damp, lambda_max, B, B2, nu, nullptr, it);
             count_launch(3);

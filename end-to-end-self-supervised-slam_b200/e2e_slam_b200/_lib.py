@@ -52,7 +52,11 @@ _SIGNATURES = {
     "e2e_fusion_associate": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P]),
     "e2e_fusion_workspace_bytes": (_SZ, [_I, _I]),
     "e2e_fusion_merge_append": (_I, [_P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _SZ, _P]),
-    "e2e_icp_workspace_bytes": (_SZ, [_LL]),
+    "e2e_knn1_grid_workspace_bytes": (_SZ, [_LL]),
+    "e2e_knn1_grid_fwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _SZ, _P]),
+    "e2e_knn1_grid_build": (_I, [_P, _LL, _P, _SZ, _P]),
+    "e2e_knn1_grid_query": (_I, [_P, _P, _LL, _LL, _P, _P, _P, _P]),
+    "e2e_icp_workspace_bytes": (_SZ, [_LL, _LL]),
     "e2e_icp_point_to_plane": (_I, [_P, _LL, _P, _P, _LL, _P, _I, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P, _SZ, _P]),
     "e2e_fusion_sequence_workspace_bytes": (_SZ, [_I, _I, _LL]),
     "e2e_fusion_sequence": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _LL, _LL, _P, _SZ, _P]),

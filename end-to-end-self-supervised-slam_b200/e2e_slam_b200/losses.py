@@ -5,6 +5,8 @@ behaviour, backed by the CUDA kernels (no chamferdist / matplotlib imports neede
     geometric_consistency_loss, knn_points_loss, color_points_loss, depth_metrics, compute_depth_errors
 plus `smoothness_loss(disp, img)`, the fused form of compute_smoothness_loss (train_depth.py:763-773).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -193,6 +195,15 @@ from collections import namedtuple  # noqa: E402
 _KNN = namedtuple("KNN", "dists idx knn")
 
 
+KNN_MODE = os.environ.get("E2E_KNN", "auto")        # "auto" | "brute" | "grid" (tests and A/B timing)
+
+
+def _use_grid(P1, P2):
+    if KNN_MODE == "auto":
+        return P1 * P2 >= (1 << 24)                  # measured: 19 200 x 75 000 -> grid 0.15 ms, brute force 5.7 ms
+    return KNN_MODE == "grid"
+
+
 class _KNN1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, query, ref, transform):
@@ -203,7 +214,13 @@ class _KNN1(torch.autograd.Function):
         dist2 = torch.empty(P1, dtype=torch.float32, device=q.device)
         idx = torch.empty(P1, dtype=torch.int64, device=q.device)
         with torch.cuda.device(q.device):
-            check(lib().e2e_knn1_fwd(ptr(q), ptr(t), ptr(r), P1, P2, ptr(dist2), ptr(idx), stream_ptr()), "e2e_knn1_fwd")
+            if _use_grid(P1, P2):      # same answer bit for bit, cost ~ P1 + P2 instead of P1 * P2
+                nws = lib().e2e_knn1_grid_workspace_bytes(P2)
+                ws = torch.empty(nws, dtype=torch.uint8, device=q.device)
+                check(lib().e2e_knn1_grid_fwd(ptr(q), ptr(t), ptr(r), P1, P2, ptr(dist2), ptr(idx), ptr(ws), nws, stream_ptr()),
+                      "e2e_knn1_grid_fwd")
+            else:
+                check(lib().e2e_knn1_fwd(ptr(q), ptr(t), ptr(r), P1, P2, ptr(dist2), ptr(idx), stream_ptr()), "e2e_knn1_fwd")
         ctx.save_for_backward(q, r, idx) if t is None else ctx.save_for_backward(q, r, idx, t)
         ctx.mark_non_differentiable(idx)
         return dist2, idx

@@ -4,7 +4,7 @@
 (configs/config.yaml:30-34; train_depth.py:111-116, 378-381; online_adaption.py:362-363).
 
 Two routes, same conventions (frozen in oracle/icp_oracle.py; gradslam itself is not vendored by the reference):
-  * no autograd: the whole iteration loop runs inside the library (e2e_icp_point_to_plane: exact brute-force kNN, fused
+  * no autograd: the whole iteration loop runs inside the library (e2e_icp_point_to_plane: exact grid kNN (target gridded once per call), fused
     Jacobian + normal equations, device-side 6x6 solve and se3 exponential, no host synchronisation);
   * autograd (GradICP's purpose: poses differentiable w.r.t. the live depth): the same iteration written with torch
     ops around the library's kNN kernel (the correspondences are constants, as in gradslam).
@@ -87,7 +87,7 @@ def _library_icp(src_pc, tgt_pc, tgt_normals, initial_transform, numiters, damp,
     N, M = src.shape[0], tgt.shape[0]
     T_out = torch.empty(4, 4, dtype=torch.float32, device=dev)
     idx = torch.empty(N, dtype=torch.int64, device=dev)
-    nws = lib().e2e_icp_workspace_bytes(N)
+    nws = lib().e2e_icp_workspace_bytes(N, M)
     ws = torch.empty(nws, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib().e2e_icp_point_to_plane(ptr(src), N, ptr(tgt), ptr(nrm), M, ptr(T0), int(numiters), ctypes.c_float(damp),

@@ -274,6 +274,17 @@ int e2e_knn1_fwd(const float *query, const float *transform, const float *ref, l
 int e2e_knn1_bwd(const float *query, const float *transform, const float *ref, long long P1, long long P2,
                  const long long *idx, const float *grad_dist2, float *grad_query, float *grad_ref, void *stream);
 
+/* The same answer (bit for bit: distances in the same operation order, lowest index among exact ties) through a uniform grid
+ * over the reference cloud, built on the device by the call itself; cost grows with P1 + P2 instead of P1 * P2.  The host
+ * side uses it when P1 * P2 is large (the online loop's point supervision: 307 200 queries against a map of millions). */
+size_t e2e_knn1_grid_workspace_bytes(long long P2);
+/* build once, query many times against the same reference cloud (the workspace IS the grid) */
+int e2e_knn1_grid_build(const float *ref, long long P2, void *workspace, size_t workspace_bytes, void *stream);
+int e2e_knn1_grid_query(const float *query, const float *transform, long long P1, long long P2,
+                        float *dist2, long long *idx, const void *workspace, void *stream);
+int e2e_knn1_grid_fwd(const float *query, const float *transform, const float *ref, long long P1, long long P2,
+                      float *dist2, long long *idx, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Point-to-plane ICP / GradICP odometry (gradslam PointFusion with odom = "icp" / "gradicp", the reference's shipped
  * default: configs/config.yaml:30-34; constructed at train_depth.py:111-116, stepped at online_adaption.py:362-363,
@@ -282,10 +293,11 @@ int e2e_knn1_bwd(const float *query, const float *transform, const float *ref, l
  * src [N,3], tgt / tgt_normals [M,3], T_init / T_out device 4x4 row-major.  The iteration loop runs without host
  * synchronisation (state on the device).  dist_thresh < 0: keep every pair; otherwise pairs with SQUARED distance below
  * it.  grad_icp = 0: Gauss-Newton with fixed damping `damp`; 1: logistic-gated Levenberg-Marquardt (lambda_max, B, B2,
- * nu; conventions in oracle/icp_oracle.py).  idx_out (nullable) [N] int64: correspondences of the last linearisation;
+ * nu; conventions in oracle/icp_oracle.py).  The target cloud is gridded once per call (e2e_knn1_grid_build) and queried
+ * every iteration.  idx_out (nullable) [N] int64: correspondences of the last linearisation;
  * errs (nullable) [numiters] fp32: |b|^2 before every step.
  * --------------------------------------------------------------------------------------------- */
-size_t e2e_icp_workspace_bytes(long long N);
+size_t e2e_icp_workspace_bytes(long long N, long long M);
 int e2e_icp_point_to_plane(const float *src, long long N, const float *tgt, const float *tgt_normals, long long M,
                            const float *T_init, int numiters, float damp, float dist_thresh,
                            int grad_icp, float lambda_max, float B, float B2, float nu,

@@ -341,3 +341,81 @@ def test_sequence_entry_continues_an_existing_map(H, W):
     assert n == int(part[4][0]) and n > (depth[0] > 0).sum()
     for a, b in zip(whole[:4], part[:4]):
         assert torch.equal(a[:n], b[:n])
+
+
+def _knn_both(q, r, T=None):
+    """(dist2, idx) from the brute-force kernel and from the grid kernel, through the C ABI."""
+    import ctypes
+    from e2e_slam_b200._lib import check, lib, ptr, stream_ptr
+    q, r = q.contiguous(), r.contiguous()
+    P1, P2 = q.shape[0], r.shape[0]
+    out = []
+    for grid in (False, True):
+        d2 = torch.empty(P1, dtype=torch.float32, device="cuda")
+        idx = torch.empty(P1, dtype=torch.int64, device="cuda")
+        if grid:
+            nws = lib().e2e_knn1_grid_workspace_bytes(P2)
+            ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+            check(lib().e2e_knn1_grid_fwd(ptr(q), ptr(T), ptr(r), P1, P2, ptr(d2), ptr(idx), ptr(ws), nws, stream_ptr()), "grid")
+        else:
+            check(lib().e2e_knn1_fwd(ptr(q), ptr(T), ptr(r), P1, P2, ptr(d2), ptr(idx), stream_ptr()), "brute")
+        out.append((d2, idx))
+    return out
+
+
+@pytest.mark.parametrize("case", ["uniform", "surface", "clustered", "duplicates", "far_queries", "line", "single", "nonfinite"])
+def test_grid_knn_equals_brute_force(case):
+    """The uniform-grid kernel must return the brute-force kernel's answer bit for bit (same distance arithmetic, lowest
+    index among exact ties) whatever the shape of the clouds."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rnd = lambda *s: torch.rand(*s, generator=g, device="cuda")
+    T = None
+    if case == "uniform":
+        q, r = rnd(20011, 3) * 4, rnd(50021, 3) * 4
+    elif case == "surface":                     # a depth-map like sheet: the real use (live frame vs. map), with a fused transform
+        uv = rnd(60000, 2) * 4 - 2
+        r = torch.stack([uv[:, 0], uv[:, 1], 2.5 + 0.3 * torch.sin(2 * uv[:, 0]) * torch.cos(uv[:, 1])], 1) + 0.002 * rnd(60000, 3)
+        q = r[torch.randperm(60000, device="cuda", generator=g)[:15000]] + 0.01 * (rnd(15000, 3) - 0.5)
+        T = torch.eye(4, device="cuda"); T[:3, 3] = torch.tensor([0.01, -0.02, 0.015], device="cuda"); T[0, 1], T[1, 0] = -0.01, 0.01
+    elif case == "clustered":                   # a few dense blobs and a lot of empty space
+        c = rnd(7, 3) * 50
+        r = (c[torch.randint(0, 7, (40000,), device="cuda", generator=g)] + 0.05 * (rnd(40000, 3) - 0.5))
+        q = rnd(9000, 3) * 50
+    elif case == "duplicates":                  # many exact ties: the lowest index must win
+        base = rnd(300, 3)
+        r = base[torch.randint(0, 300, (20000,), device="cuda", generator=g)]
+        q = torch.cat([base, rnd(3000, 3)])
+    elif case == "far_queries":                 # queries far outside the reference box, on every side
+        r = rnd(30000, 3)
+        q = torch.cat([rnd(2000, 3) * 200 - 100, rnd(500, 3)])
+    elif case == "line":                        # degenerate extent on two axes
+        r = torch.zeros(25000, 3, device="cuda"); r[:, 0] = rnd(25000) * 10
+        q = torch.zeros(4000, 3, device="cuda"); q[:, 0] = rnd(4000) * 12 - 1; q[:, 1] = 0.01 * rnd(4000)
+    elif case == "single":
+        r, q = rnd(1, 3), rnd(100, 3) * 5
+    else:                                       # NaN / inf on either side never match; all-NaN queries answer (inf, 0) like brute force
+        r = rnd(5000, 3); r[17] = float("nan"); r[99, 1] = float("inf")
+        q = rnd(600, 3); q[3, 2] = float("nan"); q[40] = float("inf")
+    (d_b, i_b), (d_g, i_g) = _knn_both(q, r, T)
+    assert torch.equal(i_b, i_g), f"indices differ at {int((i_b != i_g).sum())} of {q.shape[0]} queries"
+    assert torch.equal(d_b.view(torch.int32), d_g.view(torch.int32))
+
+
+def test_grid_knn_full_size_point_supervision():
+    """Config C2 / online_adaption shape: one live frame (307 200 points, moved by a small transform) against a 2 M-point
+    map.  Brute force would be 6e11 pairs; the grid answer is checked against a float64 KD-tree."""
+    from scipy.spatial import cKDTree
+    from e2e_slam_b200 import losses
+    g = torch.Generator(device="cuda").manual_seed(5)
+    uv = torch.rand(2_000_000, 2, generator=g, device="cuda") * 8 - 4
+    r = torch.stack([uv[:, 0], uv[:, 1], 3.0 + 0.4 * torch.sin(uv[:, 0]) * torch.cos(1.3 * uv[:, 1])], 1)
+    sel = torch.randperm(2_000_000, device="cuda", generator=g)[:307_200]
+    q = (r[sel] + 0.01 * (torch.rand(307_200, 3, generator=g, device="cuda") - 0.5)).requires_grad_(True)
+    T = torch.eye(4, device="cuda"); T[:3, 3] = torch.tensor([0.02, -0.01, 0.03], device="cuda")
+    assert losses._use_grid(q.shape[0], r.shape[0])
+    loss = losses.point_supervision_loss(q, T, r)
+    loss.backward()
+    qt = (q.detach() @ T[:3, :3].t() + T[:3, 3]).cpu().double().numpy()
+    d, i = cKDTree(r.cpu().double().numpy()).query(qt)
+    assert abs(float(loss) - float((d ** 2).mean())) <= 1e-5 * float((d ** 2).mean())
+    assert bool(torch.isfinite(q.grad).all()) and float(q.grad.abs().sum()) > 0
