@@ -42,6 +42,9 @@ def photometric_loss(ssim, prediction, target):
     return 0.85 * ssim_loss + 0.15 * torch.abs(target - prediction).mean(1, True)
 
 
+_SMOOTH_FUSED = os.environ.get("E2E_SMOOTH_FUSED", "1") != "0"
+
+
 class _Smooth(torch.autograd.Function):
     @staticmethod
     def forward(ctx, disp, img):
@@ -51,6 +54,17 @@ class _Smooth(torch.autograd.Function):
         B, _, H, W = disp.shape
         disp_c = disp.contiguous()
         loss = torch.empty(1, dtype=torch.float32, device=disp.device)
+        ctx.fused = bool(ctx.needs_input_grad[0]) and _SMOOTH_FUSED and H >= 2 and W >= 2
+        if ctx.fused:        # value and d loss / d n in one sweep; backward is one elementwise pass
+            gn = torch.empty_like(disp_c)
+            stats = torch.empty(B, 2, dtype=torch.float32, device=disp.device)
+            n = lib().e2e_smooth_vg_workspace_bytes(B, H, W)
+            ws = torch.empty(n, dtype=torch.uint8, device=disp.device)
+            with torch.cuda.device(disp.device):
+                check(lib().e2e_smooth_vg(ptr(disp_c), ptr(img), strides4(img), B, H, W, ptr(loss), ptr(gn), ptr(stats), ptr(ws), n,
+                                          stream_ptr()), "e2e_smooth_vg")
+            ctx.save_for_backward(gn, stats)
+            return loss.reshape(())
         ws, n = _red_ws(disp.device)
         with torch.cuda.device(disp.device):
             check(lib().e2e_smooth_fwd(ptr(disp_c), ptr(img), strides4(img), B, H, W, ptr(loss), ptr(ws), n, stream_ptr()),
@@ -60,6 +74,14 @@ class _Smooth(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.fused:
+            gn, stats = ctx.saved_tensors
+            B, _, H, W = gn.shape
+            gd = torch.empty_like(gn)
+            g = f32(g, "grad").reshape(1).contiguous()
+            with torch.cuda.device(gn.device):
+                check(lib().e2e_smooth_apply(ptr(gn), ptr(stats), ptr(g), B, H, W, ptr(gd), stream_ptr()), "e2e_smooth_apply")
+            return gd, None
         disp, img = ctx.saved_tensors
         B, _, H, W = disp.shape
         gd = torch.empty_like(disp)
