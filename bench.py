@@ -62,7 +62,9 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi polled every 20 ms from the start of the run (it needs ~0.2 s to emit its first line, longer than the
+    timed region); stop(t0, t1) keeps the samples whose timestamps fall inside the timed region [t0, t1] (host clock)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -73,7 +75,8 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -84,22 +87,26 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().strip().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 6:
+            if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), [n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t0 is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        window = "timed region"
+        if not inside:           # shorter than one polling interval: the samples around it (same load: warm-up runs the same step)
+            inside = [r for r in rows if t0 is not None and t0 - 0.25 <= r[0] <= t1 + 0.25] or rows
+            window = "timed region +- 0.25 s"
+        if inside:
+            out = {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                   "reasons": sorted({n for r in inside for n in r[3]}), "samples": len(inside), "window": window}
         return out
 
 
@@ -166,6 +173,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     P = args.pairs_per_gpu
+    clocks = ClockSampler(local) if rank == 0 else None
 
     # ---- synthetic inputs, resident in HBM (2.2 GB per GPU >> 126 MB L2) ------------------------------
     chunks = [make_pairs(min(32, P - s), H, W, "icl", seed=1000 * rank + s, device=dev) for s in range(0, P, 32)]
@@ -218,19 +226,20 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(None)
     sync_all()
-    clocks = ClockSampler(local) if rank == 0 else None
     launches0 = ops.launch_count()
     recs = []
     t_start, t_end = ev(), ev()
+    wall0 = time.time()
     t_start.record()
     for _ in range(args.steps):
         loss = step(recs)
     t_end.record()
     sync_all()
+    wall1 = time.time()
     launches = ops.launch_count() - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     vg_ms = [e0.elapsed_time(e1) for e0, e1 in recs]
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(wall0, wall1) if clocks else None
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
