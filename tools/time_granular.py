@@ -53,3 +53,44 @@ with torch.no_grad():
     print(f"{'granular chain fwd':24s} {t:7.3f} ms  {npx / t / 1e6:6.2f} Gpx/s")
 t = timeit(lambda: chain(True))
 print(f"{'granular chain fwd+bwd':24s} {t:7.3f} ms  {npx / t / 1e6:6.2f} Gpx/s   (the unmodified scripts' call sequence; the fused op does this in one sweep)")
+
+
+def fb(name, make, bpp):
+    def run():
+        out, leaves = make()
+        out.mean().backward()
+    t = timeit(run)
+    print(f"{name:24s} {t:7.3f} ms  {bpp * npx / t / 1e6:6.0f} GB/s ({bpp} B/px fwd+bwd incl. autograd mean)")
+
+
+def mk_ssim():
+    a = syn.detach().requires_grad_(True)
+    return ssim(a, tgt), (a,)
+
+
+def mk_photo():
+    a = syn.detach().requires_grad_(True)
+    return losses.photometric_loss(ssim, a, tgt), (a,)
+
+
+def mk_gs():
+    s = src.detach().requires_grad_(True)
+    g = pix.detach().requires_grad_(True)
+    return view_synthesis.grid_sample(s, g, padding_mode="border", align_corners=False), (s, g)
+
+
+def mk_proj():
+    p_ = pts.detach().requires_grad_(True)
+    return pr(p_, d["K"], d["T"], False)[0], (p_,)
+
+
+def mk_bp():
+    dd = d["depth"].detach().requires_grad_(True)
+    return bp(dd, d["inv_K"]), (dd,)
+
+
+fb("SSIM fwd+bwd", mk_ssim, 36 + 36)
+fb("photometric fwd+bwd", mk_photo, 28 + 28)
+fb("grid_sample fwd+bwd", mk_gs, 32 + 44)
+fb("project3d fwd+bwd", mk_proj, 28 + 24)
+fb("backproject fwd+bwd", mk_bp, 20 + 20)
