@@ -223,6 +223,26 @@ __global__ void __launch_bounds__(RED_NT) ew_bwd_kernel(const float *a, const fl
     }
 }
 
+// d loss / d {warped, interpolated} of geometric_consistency_loss: loss = sum(t * m) / sum(m) if sum(m) > 10000 else 0,
+// t = clamp(|a - b| / (a + b), 0, 1) (clamp passes the gradient on the closed interval, like torch.clamp)
+__global__ void __launch_bounds__(RED_NT) geometric_bwd_kernel(const float *a, const float *b, const float *m, long long n,
+                                                               const float *mask_sum, const float *grad_loss, float *ga, float *gb)
+{
+    const float cnt = mask_sum[0];
+    const float g = (cnt > 10000.0f) ? (grad_loss ? grad_loss[0] : 1.0f) / cnt : 0.0f;
+    for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT) {
+        const float d = a[i] - b[i], s = a[i] + b[i], t = fabsf(d) / s;
+        float da = 0.f, db = 0.f;
+        if (g != 0.0f && t >= 0.f && t <= 1.f) {
+            const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f), q = fabsf(d) / (s * s);
+            da = g * m[i] * (sg / s - q);
+            db = g * m[i] * (-sg / s - q);
+        }
+        if (ga) ga[i] = da;
+        if (gb) gb[i] = db;
+    }
+}
+
 static int check_ws(void *ws, size_t bytes, size_t need)
 {
     E2E_REQUIRE(ws && bytes >= need, "workspace too small: need %zu bytes, got %zu", need, bytes);
@@ -347,6 +367,16 @@ int e2e_geometric_fwd(const float *warped_depth, const float *interp_depth, cons
 {
     E2E_REQUIRE(valid, "geometric: null valid mask");
     return ew_fwd<EW_GEOMETRIC>(warped_depth, interp_depth, valid, n, loss, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int e2e_geometric_bwd(const float *warped_depth, const float *interp_depth, const float *valid, long long n, const float *mask_sum,
+                      const float *grad_loss, float *grad_warped, float *grad_interp, void *stream)
+{
+    E2E_REQUIRE(warped_depth && interp_depth && valid && mask_sum && (grad_warped || grad_interp) && n > 0, "geometric_bwd: bad arguments");
+    geometric_bwd_kernel<<<red_blocks(n), RED_NT, 0, (cudaStream_t)stream>>>(warped_depth, interp_depth, valid, n, mask_sum, grad_loss,
+                                                                             grad_warped, grad_interp);
+    count_launch();
+    return finish_launch("geometric_bwd");
 }
 
 }  // extern "C"

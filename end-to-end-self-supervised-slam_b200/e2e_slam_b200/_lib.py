@@ -50,6 +50,7 @@ _SIGNATURES = {
     "e2e_depth_reg_fwd": (_I, [_P, _P, _LL, _I, _P, _P, _SZ, _P]),
     "e2e_depth_reg_bwd": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
     "e2e_geometric_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
+    "e2e_geometric_bwd": (_I, [_P, _P, _P, _LL, _P, _P, _P, _P, _P]),
     "e2e_rgbd_maps": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     "e2e_rgbd_maps_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     "e2e_fusion_associate": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P]),

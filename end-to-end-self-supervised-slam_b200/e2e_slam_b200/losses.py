@@ -168,18 +168,40 @@ def depth_gt_loss(prediction, sparse_groundtruth, sparse_mask):
     return _EwLoss.apply("sparse", p.contiguous(), m.detach().contiguous(), g.detach().contiguous())
 
 
+class _Geometric(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wd, idp, mask):
+        wd_c, id_c, m_c = wd.contiguous(), idp.contiguous(), mask.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=wd.device)
+        ws, nb = _red_ws(wd.device)
+        with torch.cuda.device(wd.device):
+            check(lib().e2e_geometric_fwd(ptr(wd_c), ptr(id_c), ptr(m_c), wd_c.numel(), ptr(loss), ptr(ws), nb, stream_ptr()),
+                  "e2e_geometric_fwd")
+        ctx.save_for_backward(wd_c, id_c, m_c)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        wd, idp, m = ctx.saved_tensors
+        g = f32(g, "grad").reshape(1).contiguous()
+        msum = m.sum().reshape(1)                       # stays on the device: the > 10000 test is evaluated by the kernel
+        ga = torch.empty_like(wd) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(idp) if ctx.needs_input_grad[1] else None
+        if ga is None and gb is None:
+            return None, None, None
+        with torch.cuda.device(wd.device):
+            check(lib().e2e_geometric_bwd(ptr(wd), ptr(idp), ptr(m), wd.numel(), ptr(msum), ptr(g), ptr(ga), ptr(gb), stream_ptr()),
+                  "e2e_geometric_bwd")
+        return ga, gb, None
+
+
 def geometric_consistency_loss(outputs, frame, device):
     """clamp(|wd - id| / (wd + id), 0, 1) averaged over the valid mask if it has > 10000 pixels, else 0
-    (losses.py:84-95).  Forward-only kernel; the count test runs on the device (the reference syncs)."""
+    (losses.py:84-95), differentiable w.r.t. both depth maps.  The count test runs on the device (the reference syncs)."""
     wd, idp = outputs[("warped_depth", frame)], outputs[("interpolated_depth", frame)]
     mask = outputs[("valid_mask", frame)].expand_as(wd)
-    f32(wd, "warped_depth")
-    loss = torch.empty(1, dtype=torch.float32, device=wd.device)
-    ws, nb = _red_ws(wd.device)
-    with torch.cuda.device(wd.device):
-        check(lib().e2e_geometric_fwd(ptr(wd.detach().contiguous()), ptr(idp.detach().contiguous()), ptr(mask.contiguous()),
-                                      wd.numel(), ptr(loss), ptr(ws), nb, stream_ptr()), "e2e_geometric_fwd")
-    return loss.reshape(())
+    f32(wd, "warped_depth"), f32(idp, "interpolated_depth"), f32(mask, "valid_mask")
+    return _Geometric.apply(wd, idp, mask.detach())
 
 
 @torch.no_grad()

@@ -173,7 +173,7 @@ int e2e_grid_sample_bwd(const float *grad_output, const float *input, const int6
  *                    disp [B,1,H,W] contiguous, img 3-channel via strides.  loss [1].
  *   e2e_sparse_l1_*  depth_gt_loss (loss/losses.py:151-160): mean over all n elements of |pred*mask - gt|.
  *   e2e_depth_reg_*  depth_reguralizer (loss/losses.py:134-148): kind 1 = L1, 2 = L2 (MSE).
- *   e2e_geometric_fwd geometric_consistency_loss (loss/losses.py:84-95), forward only; the >10000
+ *   e2e_geometric_fwd geometric_consistency_loss (loss/losses.py:84-95), forward + backward; the >10000
  *                    mask-count test is evaluated on the device (no host sync).
  * Backward entry points take the upstream scalar gradient as a device pointer (NULL = 1.0).
  * --------------------------------------------------------------------------------------------- */
@@ -205,6 +205,10 @@ int e2e_depth_reg_bwd(const float *initial, const float *refined, long long n, i
 
 int e2e_geometric_fwd(const float *warped_depth, const float *interp_depth, const float *valid, long long n,
                       float *loss, void *workspace, size_t workspace_bytes, void *stream);
+/* gradients to warped / interpolated depth (either may be NULL); mask_sum = device float holding sum(valid) (the > 10000 test
+ * of loss/losses.py:90 is evaluated on the device), grad_loss = device-resident upstream scalar (NULL = 1) */
+int e2e_geometric_bwd(const float *warped_depth, const float *interp_depth, const float *valid, long long n, const float *mask_sum,
+                      const float *grad_loss, float *grad_warped, float *grad_interp, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PointFusion (gradslam semantics; gradslam itself is not vendored by the

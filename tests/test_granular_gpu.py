@@ -127,6 +127,20 @@ def test_geometric_consistency(golden):
     out = {("warped_depth", 1): wd.cuda(), ("interpolated_depth", 1): idp.cuda(), ("valid_mask", 1): valid.cuda()}
     l = geometric_consistency_loss(out, 1, torch.device("cuda"))
     assert float(ref) > 0 and abs(float(l) - float(ref)) <= RTOL * float(ref)
+    # gradients to both depth maps (the reference's term is differentiable; LOSS.geometric is off by default), incl. values
+    # that sit on the clamp and a mask below the 10000-pixel threshold (loss and gradients identically 0)
+    wd[0, 0, :3] = 3.0 * idp[0, 0, :3] + 4.0                    # |a-b|/(a+b) < 1 always for positive depths; add exact zeros instead
+    wd[0, 0, 5] = idp[0, 0, 5]
+    for vm in (valid, (torch.rand(1, 1, 200, 300) > 0.9).float()):
+        a64, b64 = wd.double().requires_grad_(True), idp.double().requires_grad_(True)
+        torch_oracle.geometric_consistency(a64, b64, vm.double()).backward() if vm.sum() > 10000 else None
+        a, b = wd.cuda().requires_grad_(True), idp.cuda().requires_grad_(True)
+        out = {("warped_depth", 1): a, ("interpolated_depth", 1): b, ("valid_mask", 1): vm.cuda()}
+        geometric_consistency_loss(out, 1, torch.device("cuda")).backward()
+        if vm.sum() > 10000:
+            assert rel_max(a.grad.cpu().numpy(), a64.grad.numpy()) <= RTOL and rel_max(b.grad.cpu().numpy(), b64.grad.numpy()) <= RTOL
+        else:
+            assert float(a.grad.abs().max()) == 0.0 and float(b.grad.abs().max()) == 0.0
 
 
 def test_smoothness_full_size():
