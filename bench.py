@@ -396,6 +396,15 @@ def run_ours(args):
                "brute_force_pairs_avoided": float(P1n) * P2n, "kernel": "uniform-grid exact kNN (bit-identical to brute force)"}
         del ref, qry, uv
 
+    # ---- secondary: config C2 refinement step (single TUM pair, full loss mix), latency eager / CUDA graph --------
+    c2 = None
+    if world == 1 and not args.skip_fusion:
+        try:
+            from e2e_slam_b200 import c2_bench
+            c2 = c2_bench.run(dev)
+        except ImportError:
+            c2 = None
+
     # ---- secondary metric: PointFusion points fused/s (config C3) ----------------------------------------
     fusion = None
     if world == 1 and not args.skip_fusion:
@@ -419,7 +428,7 @@ def run_ours(args):
                 "steps": e2e_steps, "loss": lval, "h2d_chunks": n_chunks},
         "gpu_launches": launches,
         "roofline": roof, "two_kernel_path": roof_two,
-        "cpu_baseline": cpu, "fusion": fusion, "single_pair": single, "point_supervision": knn, "loss": float(loss),
+        "cpu_baseline": cpu, "fusion": fusion, "single_pair": single, "c2_refinement_step": c2, "point_supervision": knn, "loss": float(loss),
     }
     print(json.dumps(out))
     if world > 1:
