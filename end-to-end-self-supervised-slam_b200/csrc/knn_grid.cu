@@ -382,46 +382,77 @@ __global__ void __launch_bounds__(KG_NT) kg_query_far_kernel(const float *query,
         const float hc = g.h * (float)KG_M, half = g.h * (0.5f + slack);
         // rings before the first one that can touch the grid hold nothing
         int r = max(max(max(-qX, qX - (mx - 1)), max(-qY, qY - (my - 1))), max(max(-qZ, qZ - (mz - 1)), 0));
+        int pX0 = 0, pX1 = -1, pY0 = 0, pY1 = -1, pZ0 = 0, pZ1 = -1;      // the part of the grid searched so far (empty)
         for (;; r++) {
-            const int X0 = max(qX - r, 0), X1 = min(qX + r, mx - 1);
-            const int Y0 = max(qY - r, 0), Y1 = min(qY + r, my - 1);
-            const int Z0 = max(qZ - r, 0), Z1 = min(qZ + r, mz - 1);
-            for (int Z = Z0; Z <= Z1; Z++)
-                for (int Y = Y0; Y <= Y1; Y++) {
-                    const bool face = Z == qZ - r || Z == qZ + r || Y == qY - r || Y == qY + r;
-                    for (int X = X0; X <= X1; X++) {
-                        if (!face && X != qX - r && X != qX + r) {      // interior of the shell: jump to the far x face
-                            X = min(qX + r, X1 + 1) - 1;
-                            continue;
-                        }
-                        if (coarse[(Z * my + Y) * mx + X] == 0) continue;
-                        // the coarse cell's KG_M^3 fine cells, two per lane
-                        for (int f = lane; f < KG_M * KG_M * KG_M; f += 32) {
-                            const int x = X * KG_M + (f % KG_M), y = Y * KG_M + (f / KG_M) % KG_M, z = Z * KG_M + f / (KG_M * KG_M);
-                            if (x >= g.nx || y >= g.ny || z >= g.nz) continue;
-                            const int c = (z * g.ny + y) * g.nx + x;
-                            if (!((bits[c >> 5] >> (c & 31)) & 1u)) continue;
-                            const float ex = fmaxf(fabsf(qx - (g.ox + ((float)x + 0.5f) * g.h)) - half, 0.0f);
-                            const float ey = fmaxf(fabsf(qy - (g.oy + ((float)y + 0.5f) * g.h)) - half, 0.0f);
-                            const float ez = fmaxf(fabsf(qz - (g.oz + ((float)z + 0.5f) * g.h)) - half, 0.0f);
-                            if ((ex * ex + ey * ey + ez * ez) * 0.9999f > best) continue;      // farther than the best known to this lane
-                            for (int j = start[c], e = start[c + 1]; j < e; j++) {
-                                const float4 p = sorted[j];
-                                const float dx = xsub(qx, p.x), dy = xsub(qy, p.y), dz = xsub(qz, p.z);
-                                const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
-                                const int pi = __float_as_int(p.w);
-                                if (d2 < best || (d2 == best && pi < bi)) { best = d2; bi = pi; }
-                            }
-                        }
-                        // merge: minimum of (distance, index) over the lanes, known to all of them
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                        }
+            // the coarse cells of ring r inside the grid = box(r) minus box(r - 1), enumerated as up to six slabs (a query far
+            // outside the grid would otherwise re-walk everything searched so far in every ring); the lanes test 32 cells for
+            // emptiness at a time, then the warp searches the occupied ones one after the other
+            const int X0 = max(qX - r, 0), X1 = min(qX + r, mx - 1), Y0 = max(qY - r, 0), Y1 = min(qY + r, my - 1),
+                      Z0 = max(qZ - r, 0), Z1 = min(qZ + r, mz - 1);
+            const bool fresh = pX1 < pX0 || pY1 < pY0 || pZ1 < pZ0;
+            for (int slab = 0; slab < (fresh ? 1 : 6); slab++) {
+            int sx0 = X0, sx1 = X1, sy0 = Y0, sy1 = Y1, sz0 = Z0, sz1 = Z1;
+            if (!fresh) {
+                if (slab == 0) sx1 = pX0 - 1;
+                if (slab == 1) sx0 = pX1 + 1;
+                if (slab >= 2) { sx0 = pX0; sx1 = pX1; }
+                if (slab == 2) sy1 = pY0 - 1;
+                if (slab == 3) sy0 = pY1 + 1;
+                if (slab >= 4) { sy0 = pY0; sy1 = pY1; }
+                if (slab == 4) sz1 = pZ0 - 1;
+                if (slab == 5) sz0 = pZ1 + 1;
+            }
+            const int bx = sx1 - sx0 + 1, by = sy1 - sy0 + 1, bz = sz1 - sz0 + 1;
+            const int total = (bx > 0 && by > 0 && bz > 0) ? bx * by * bz : 0;
+            for (int base = 0; base < total; base += 32) {
+                const int t = base + lane;
+                int X = 0, Y = 0, Z = 0;
+                bool hit = false;
+                if (t < total) {
+                    X = sx0 + t % bx; Y = sy0 + (t / bx) % by; Z = sz0 + t / (bx * by);
+                    hit = coarse[(Z * my + Y) * mx + X] != 0;
+                    if (hit) {      // the whole coarse cell farther than the best so far (the corners of the outer rings)?
+                        const float hh = hc * (0.5f + slack);
+                        const float ex = fmaxf(fabsf(qx - (g.ox + ((float)X + 0.5f) * hc)) - hh, 0.0f);
+                        const float ey = fmaxf(fabsf(qy - (g.oy + ((float)Y + 0.5f) * hc)) - hh, 0.0f);
+                        const float ez = fmaxf(fabsf(qz - (g.oz + ((float)Z + 0.5f) * hc)) - hh, 0.0f);
+                        hit = !((ex * ex + ey * ey + ez * ez) * 0.9999f > best);
                     }
                 }
+                unsigned todo = __ballot_sync(0xffffffffu, hit);
+                while (todo) {
+                    const int srcl = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int cX = __shfl_sync(0xffffffffu, X, srcl), cY = __shfl_sync(0xffffffffu, Y, srcl), cZ = __shfl_sync(0xffffffffu, Z, srcl);
+                    // the coarse cell's KG_M^3 fine cells, two per lane
+                    for (int f = lane; f < KG_M * KG_M * KG_M; f += 32) {
+                        const int x = cX * KG_M + (f % KG_M), y = cY * KG_M + (f / KG_M) % KG_M, z = cZ * KG_M + f / (KG_M * KG_M);
+                        if (x >= g.nx || y >= g.ny || z >= g.nz) continue;
+                        const int c = (z * g.ny + y) * g.nx + x;
+                        if (!((bits[c >> 5] >> (c & 31)) & 1u)) continue;
+                        const float ex = fmaxf(fabsf(qx - (g.ox + ((float)x + 0.5f) * g.h)) - half, 0.0f);
+                        const float ey = fmaxf(fabsf(qy - (g.oy + ((float)y + 0.5f) * g.h)) - half, 0.0f);
+                        const float ez = fmaxf(fabsf(qz - (g.oz + ((float)z + 0.5f) * g.h)) - half, 0.0f);
+                        if ((ex * ex + ey * ey + ez * ez) * 0.9999f > best) continue;      // farther than the best known to this lane
+                        for (int j = start[c], e = start[c + 1]; j < e; j++) {
+                            const float4 p = sorted[j];
+                            const float dx = xsub(qx, p.x), dy = xsub(qy, p.y), dz = xsub(qz, p.z);
+                            const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+                            const int pi = __float_as_int(p.w);
+                            if (d2 < best || (d2 == best && pi < bi)) { best = d2; bi = pi; }
+                        }
+                    }
+                    // merge: minimum of (distance, index) over the lanes, known to all of them
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                }
+            }
+            }      // slabs
+            pX0 = X0; pX1 = X1; pY0 = Y0; pY1 = Y1; pZ0 = Z0; pZ1 = Z1;
             const float reach = ((float)r - slack) * hc;
             if (reach > 0.0f && best <= reach * reach) break;
             if (qX - r <= 0 && qX + r >= mx - 1 && qY - r <= 0 && qY + r >= my - 1 && qZ - r <= 0 && qZ + r >= mz - 1) break;

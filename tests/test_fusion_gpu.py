@@ -363,7 +363,8 @@ def _knn_both(q, r, T=None):
     return out
 
 
-@pytest.mark.parametrize("case", ["uniform", "surface", "clustered", "duplicates", "far_queries", "line", "single", "nonfinite"])
+@pytest.mark.parametrize("case", ["uniform", "surface", "clustered", "duplicates", "far_queries", "all_far", "off_surface", "line", "single",
+                                  "nonfinite"])
 def test_grid_knn_equals_brute_force(case):
     """The uniform-grid kernel must return the brute-force kernel's answer bit for bit (same distance arithmetic, lowest
     index among exact ties) whatever the shape of the clouds."""
@@ -388,6 +389,14 @@ def test_grid_knn_equals_brute_force(case):
     elif case == "far_queries":                 # queries far outside the reference box, on every side
         r = rnd(30000, 3)
         q = torch.cat([rnd(2000, 3) * 200 - 100, rnd(500, 3)])
+    elif case == "all_far":                     # every query far outside the reference box (a wrong pose): must stay cheap
+        r = rnd(30000, 3)
+        q = rnd(20000, 3) + torch.tensor([40.0, -25.0, 60.0], device="cuda")
+    elif case == "off_surface":                 # queries several cell sizes off a dense sheet (a noisy depth prediction)
+        uv = rnd(200000, 2) * 2 - 1
+        r = torch.stack([uv[:, 0], uv[:, 1], 2.0 + 0.2 * torch.sin(3 * uv[:, 0])], 1)
+        q = r[torch.randperm(200000, device="cuda", generator=g)[:30000]].clone()
+        q[:, 2] += 0.1 * torch.randn(30000, generator=g, device="cuda")
     elif case == "line":                        # degenerate extent on two axes
         r = torch.zeros(25000, 3, device="cuda"); r[:, 0] = rnd(25000) * 10
         q = torch.zeros(4000, 3, device="cuda"); q[:, 0] = rnd(4000) * 12 - 1; q[:, 1] = 0.01 * rnd(4000)
