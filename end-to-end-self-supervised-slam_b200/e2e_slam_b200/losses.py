@@ -248,6 +248,26 @@ def _use_grid(P1, P2):
     return KNN_MODE == "grid"
 
 
+_GRID_CACHE = {}
+
+
+def _grid_for(ref):
+    """The grid over a reference cloud, rebuilt only when the cloud changes: the global map is the same tensor for every
+    refinement step on a key-frame (online_adaption.py:638-645 detaches it).  The entry keeps the tensor alive, so its
+    storage address cannot be recycled, and any in-place write bumps the version counter that is part of the key."""
+    key = (ref.untyped_storage().data_ptr(), ref.storage_offset(), tuple(ref.shape), tuple(ref.stride()), ref._version, ref.device)
+    hit = _GRID_CACHE.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[2]
+    _GRID_CACHE.pop("last", None)                     # free the old grid before allocating the new one
+    P2 = ref.shape[0]
+    nws = lib().e2e_knn1_grid_workspace_bytes(P2)
+    ws = torch.empty(nws, dtype=torch.uint8, device=ref.device)
+    check(lib().e2e_knn1_grid_build(ptr(ref), P2, ptr(ws), nws, stream_ptr()), "e2e_knn1_grid_build")
+    _GRID_CACHE["last"] = (key, ref, ws)
+    return ws
+
+
 class _KNN1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, query, ref, transform):
@@ -259,10 +279,9 @@ class _KNN1(torch.autograd.Function):
         idx = torch.empty(P1, dtype=torch.int64, device=q.device)
         with torch.cuda.device(q.device):
             if _use_grid(P1, P2):      # same answer bit for bit, cost ~ P1 + P2 instead of P1 * P2
-                nws = lib().e2e_knn1_grid_workspace_bytes(P2)
-                ws = torch.empty(nws, dtype=torch.uint8, device=q.device)
-                check(lib().e2e_knn1_grid_fwd(ptr(q), ptr(t), ptr(r), P1, P2, ptr(dist2), ptr(idx), ptr(ws), nws, stream_ptr()),
-                      "e2e_knn1_grid_fwd")
+                ws = _grid_for(r)
+                check(lib().e2e_knn1_grid_query(ptr(q), ptr(t), P1, P2, ptr(dist2), ptr(idx), ptr(ws), stream_ptr()),
+                      "e2e_knn1_grid_query")
             else:
                 check(lib().e2e_knn1_fwd(ptr(q), ptr(t), ptr(r), P1, P2, ptr(dist2), ptr(idx), stream_ptr()), "e2e_knn1_fwd")
         ctx.save_for_backward(q, r, idx) if t is None else ctx.save_for_backward(q, r, idx, t)

@@ -428,3 +428,28 @@ def test_grid_knn_full_size_point_supervision():
     d, i = cKDTree(r.cpu().double().numpy()).query(qt)
     assert abs(float(loss) - float((d ** 2).mean())) <= 1e-5 * float((d ** 2).mean())
     assert bool(torch.isfinite(q.grad).all()) and float(q.grad.abs().sum()) > 0
+
+
+def test_grid_cache_follows_the_reference_cloud(monkeypatch):
+    """The grid over the reference cloud is reused while the cloud is unchanged and rebuilt after an in-place write or for
+    another tensor (a stale grid would silently return wrong neighbours)."""
+    from e2e_slam_b200 import losses
+    monkeypatch.setattr(losses, "KNN_MODE", "grid")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    r = torch.rand(5000, 3, generator=g, device="cuda")
+    q = torch.rand(700, 3, generator=g, device="cuda")
+
+    def brute(ref):
+        d = ((q[:, None, :] - ref[None, :, :]) ** 2).sum(-1)
+        return d.argmin(1)
+
+    i1 = losses.knn_points(q[None], r[None]).idx[0, :, 0]
+    ws1 = losses._GRID_CACHE["last"][2]
+    i2 = losses.knn_points(q[None], r[None].detach()).idx[0, :, 0]            # a new tensor object over the same storage: reused
+    assert losses._GRID_CACHE["last"][2] is ws1 and torch.equal(i1, i2) and torch.equal(i1, brute(r))
+    r[:2500] += 0.37                                                          # in-place change: the version counter moves
+    i3 = losses.knn_points(q[None], r[None]).idx[0, :, 0]
+    assert losses._GRID_CACHE["last"][2] is not ws1 and torch.equal(i3, brute(r))
+    r2 = torch.rand(5000, 3, generator=g, device="cuda")                      # another cloud of the same shape
+    i4 = losses.knn_points(q[None], r2[None]).idx[0, :, 0]
+    assert torch.equal(i4, brute(r2))
