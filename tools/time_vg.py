@@ -8,7 +8,8 @@ from e2e_slam_b200 import ops
 from e2e_slam_b200.synthetic import make_pairs
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-H, W = 480, 640
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 480
+W = int(sys.argv[4]) if len(sys.argv) > 4 else 640
 dev = torch.device("cuda:0")
 chunks = [make_pairs(min(32, P - s), H, W, "icl", seed=s, device=dev) for s in range(0, P, 32)]
 d = {k: torch.cat([c[k] for c in chunks]) for k in chunks[0]}
