@@ -96,7 +96,46 @@ DivC host_divc(float d, cudaStream_t stream)
 
 }  // namespace e2e
 
+namespace e2e {
+
+// 8-bit frames -> the reference's float frames: colors /= 255.0 (train_depth.py:255, online_adaption.py:215) done on the
+// device, correctly rounded division like the host's, so only a quarter of the bytes cross PCIe.
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const uchar4 *in, long long n4, float4 *out)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const uchar4 v = in[i];
+        out[i] = make_float4(__fdiv_rn((float)v.x, 255.0f), __fdiv_rn((float)v.y, 255.0f), __fdiv_rn((float)v.z, 255.0f),
+                             __fdiv_rn((float)v.w, 255.0f));
+    }
+}
+__global__ void u8_to_unit_tail_kernel(const unsigned char *in, long long from, long long n, float *out)
+{
+    const long long i = from + threadIdx.x;
+    if (i < n) out[i] = __fdiv_rn((float)in[i], 255.0f);
+}
+
+}  // namespace e2e
+
 extern "C" {
+
+int e2e_u8_to_unit(const unsigned char *in, long long n, float *out, void *stream)
+{
+    E2E_REQUIRE(in && out && n > 0, "u8_to_unit: bad arguments");
+    E2E_REQUIRE((((uintptr_t)in) & 3) == 0 && (((uintptr_t)out) & 15) == 0, "u8_to_unit: input must be 4-byte, output 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n4 = n / 4;
+    if (n4 > 0) {
+        long long blocks = (n4 + 255) / 256;
+        if (blocks > e2e::kNumSMs * 16) blocks = e2e::kNumSMs * 16;
+        e2e::u8_to_unit_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uchar4 *)in, n4, (float4 *)out);
+        e2e::count_launch();
+    }
+    if (n4 * 4 < n) {
+        e2e::u8_to_unit_tail_kernel<<<1, 4, 0, st>>>(in, n4 * 4, n, out);
+        e2e::count_launch();
+    }
+    return e2e::finish_launch("u8_to_unit");
+}
 
 int e2e_abi_version(void) { return 1; }
 const char *e2e_last_error(void) { return e2e::g_err; }

@@ -320,6 +320,21 @@ def photometric_map(prediction, target):
     return 0.85 * ssim_map(prediction, target).mean(1, True) + 0.15 * torch.abs(target - prediction).mean(1, True)
 
 
+def colors_from_uint8(frames_u8):
+    """uint8 frames (any shape, contiguous, CUDA) -> float32 frames in [0, 1]: the reference's host-side `colors /= 255.0`
+    (train_depth.py:255) done on the device, bit-identical to it, so that frames cross PCIe as bytes."""
+    if frames_u8.dtype != torch.uint8:
+        raise TypeError(f"expected a uint8 tensor, got {frames_u8.dtype}")
+    if not frames_u8.is_cuda:
+        raise _lib.E2ELibraryError("colors_from_uint8 needs a CUDA tensor (there is no CPU path)")
+    src = frames_u8.contiguous()
+    out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    if src.numel():
+        with torch.cuda.device(src.device):
+            check(lib().e2e_u8_to_unit(ptr(src), src.numel(), ptr(out), stream_ptr()), "e2e_u8_to_unit")
+    return out
+
+
 def launch_count():
     return _lib.launch_count()
 

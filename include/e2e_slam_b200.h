@@ -43,6 +43,11 @@ unsigned long long e2e_launch_count(void);
  * first time a divisor is seen.  Returns 1 (fast path exact), 0 (IEEE fallback) or <0 on error. */
 int e2e_prepare_divisor(float d, void *stream);
 
+/* 8-bit frames -> unit-range fp32 frames, out[i] = RN(in[i] / 255): the reference's host-side `colors /= 255.0`
+ * (train_depth.py:255, online_adaption.py:215) moved to the device (bit-identical: one correctly rounded division), so a
+ * frame crosses PCIe as 3 bytes per pixel instead of 12.  `in` 4-byte aligned, `out` 16-byte aligned. */
+int e2e_u8_to_unit(const unsigned char *in, long long n, float *out, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused inverse warp + photometric loss.  Replaces, in one forward and one backward kernel:
  *   BackprojectDepth.forward   depth_estimation/view_synthesis.py:34-40

@@ -201,3 +201,18 @@ def test_fused_driver_methods_on_goldens(golden):
     assert same_values(photometric.detach().cpu().numpy(), g["loss_map"]) == 0
     assert abs(float(loss.detach()) - float(g["loss"])) <= RTOL * float(g["loss"])
     assert_grad_close("g_depth", depth.grad.cpu().numpy(), g["g_depth"], g["g_depth_f64"])
+
+
+def test_colors_from_uint8_is_the_hosts_division():
+    """`colors /= 255.0` (train_depth.py:255) on the device: every one of the 256 byte values, and odd lengths, bit for bit."""
+    from e2e_slam_b200.ops import colors_from_uint8
+    allv = torch.arange(256, dtype=torch.uint8)
+    assert torch.equal(colors_from_uint8(allv.cuda()).cpu(), allv.float() / 255.0)
+    g = torch.Generator().manual_seed(1)
+    for shape in ((1, 2, 7, 9, 3), (3,), (1, 1, 480, 640, 3)):
+        u = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+        ref = u.float()
+        ref /= 255.0
+        assert torch.equal(colors_from_uint8(u.cuda()).cpu(), ref)
+    with pytest.raises(TypeError):
+        colors_from_uint8(torch.zeros(4).cuda())
