@@ -1117,6 +1117,11 @@ int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, co
     if (cudaMemsetAsync(p.counts, 0, align256(8 * 4096) + 256, st) != cudaSuccess) return finish_launch("fusion_sequence: memset");
     void *args[] = {(void *)&p};
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *)fusion_sequence_kernel, dim3(grid), dim3(SEQ_NT), args, 0, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge) {      // the GPU is shared (other resident kernels): per-frame launches instead
+        cudaGetLastError();
+        return fusion_sequence_loop(depth, rgb, K, poses, L, H, W, sigma, dist_th, dot_th, map_points, map_normals, map_colors,
+                                    map_ccount, n_map, n_upper, capacity, workspace, stream);
+    }
     if (e != cudaSuccess) {
         set_error("fusion_sequence: cooperative launch failed: %s", cudaGetErrorString(e));
         cudaGetLastError();
