@@ -579,6 +579,12 @@ int e2e_ssim_bwd(const float *x, const int64_t x_strides[4], const float *y, con
     if (int rc = set_views(p, x, x_strides, y, y_strides, C)) return rc;
     p.g_ssim = grad_ssim; p.g_loss_map = grad_loss_map;
     p.g_x = grad_x; p.g_y = grad_y;
+    // C == 3 and only d / d x wanted (the reference never differentiates the target): the streaming kernel
+    static const bool use_tile = [] { const char *e = getenv("E2E_BWD_TILE"); return e && e[0] == '1'; }();
+    if (C == 3 && grad_x && !grad_y && !use_tile && !(grad_ssim && grad_loss_map) && H <= 8189 && W <= 8189) {
+        const ImgView vx = p.src, vy = p.tgt;
+        if (view_fits_int32(vx, 3, H, W) && view_fits_int32(vy, 3, H, W)) return launch_ssim_stream_bwd(p, B, H, W, st);
+    }
     dim3 grid = tile_grid(B, H, W, B_TH, B_TW);
     if (C == 3) return launch_bwd<MODE_DIRECT, 3, true, false>(p, grid, st);
     grid.z = B * C;

@@ -366,5 +366,6 @@ int launch_reduce_gP(const float *partial, int ctas_per_b, int B, float *gP, cud
 // Defined in warp_photo_fused.cu: the streaming value + gradient kernel on a prepared parameter block
 size_t stream_workspace_bytes(int B, int H, int W);
 int launch_stream(WPParams &p, int B, int H, int W, float *loss_mean, float *grad_P, void *workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_ssim_stream_bwd(WPParams &p, int B, int H, int W, cudaStream_t st);
 
 }  // namespace e2e
