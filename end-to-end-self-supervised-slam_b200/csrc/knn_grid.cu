@@ -442,7 +442,9 @@ __global__ void __launch_bounds__(KG_NT) kg_query_far_kernel(const float *query,
                             if (d2 < best || (d2 == best && pi < bi)) { best = d2; bi = pi; }
                         }
                     }
-                    // merge: minimum of (distance, index) over the lanes, known to all of them
+                }
+                if (__any_sync(0xffffffffu, hit)) {
+                    // merge after every batch of 32 coarse cells: minimum of (distance, index) over the lanes, known to all of them
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
