@@ -350,7 +350,7 @@ class WarpPhotoPlan:
     """
 
     def __init__(self, B, H, W, device, padding_mode="border", photometric_mask=True, eps=1e-7,
-                 need_src_grad=True, need_pose_grad=True):
+                 need_src_grad=True, need_pose_grad=True, overlap_zero_fill=False):
         self.B, self.H, self.W = B, H, W
         self.device = torch.device(device)
         self.pad, self.mask, self.eps = _pad_code(padding_mode), int(bool(photometric_mask)), float(eps)
@@ -366,11 +366,37 @@ class WarpPhotoPlan:
         self.grad_src = torch.empty(B, 3, H, W, **f) if need_src_grad else None
         self.grad_P = torch.empty(B, 3, 4, **f) if need_pose_grad else None
         self._gs_strides = strides4(self.grad_src) if need_src_grad else None
+        # overlap_zero_fill: two grad_src buffers; while the kernel of this call accumulates into one, the other is cleared on a
+        # side stream for the next call (the kernel is issue-bound, the memset costs it nothing).  The buffer returned by a call
+        # stays valid until the next call starts, as without the option.  Not for CUDA-graph capture (the side stream is not joined).
+        self._overlap = bool(overlap_zero_fill and need_src_grad)
+        if self._overlap:
+            with torch.cuda.device(self.device):
+                self._bufs = [self.grad_src, torch.empty(B, 3, H, W, **f)]
+                self._side = torch.cuda.Stream(device=self.device)
+                self._zero_done = [torch.cuda.Event(), torch.cuda.Event()]
+                self._cur = 0
+                main = torch.cuda.current_stream(self.device)
+                for b_, e_ in zip(self._bufs, self._zero_done):
+                    b_.zero_()
+                    e_.record(main)
 
     def value_and_grad(self, depth, inv_K, K, T, src, tgt):
         """loss (device scalar) and d loss / d {depth, src, (K@T)[:3]} in ONE sweep (e2e_warp_photo_vg):
         zero-fill of grad_src + fused kernel + two tiny fixed-order reductions."""
-        if self.grad_src is not None:
+        if self._overlap:
+            main = torch.cuda.current_stream(self.device)
+            i = self._cur
+            self.grad_src = self._bufs[i]
+            main.wait_event(self._zero_done[i])
+            start = torch.cuda.Event()
+            start.record(main)                       # everything that still reads the other buffer was enqueued before this point
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(start)
+                self._bufs[1 - i].zero_()
+                self._zero_done[1 - i].record(self._side)
+            self._cur = 1 - i
+        elif self.grad_src is not None:
             self.grad_src.zero_()          # the kernel accumulates into it with red.global.add
         with torch.cuda.device(self.device):
             rc = lib().e2e_warp_photo_vg(ptr(depth), ptr(inv_K), ptr(K), ptr(T), ptr(src), strides4(src),

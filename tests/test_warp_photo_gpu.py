@@ -332,3 +332,27 @@ def test_speculative_map_path_equals_forward_plus_backward(e2e, upstream, monkey
             assert torch.equal(x, y), name
         else:
             assert rel_max(x.cpu().numpy(), y.cpu().numpy()) <= 2e-6, name
+
+
+def test_plan_overlapped_zero_fill(e2e):
+    """WarpPhotoPlan(overlap_zero_fill=True) clears the grad_src buffer of the NEXT call on a side stream while the kernel
+    of this call runs: repeated calls (changing inputs) must give the gradients of the plain plan, and the buffer a call
+    returns must stay intact until the next call."""
+    from e2e_slam_b200 import ops
+    from e2e_slam_b200.synthetic import make_pairs
+    B, H, W = 3, 60, 90
+    plain, fast = ops.WarpPhotoPlan(B, H, W, "cuda"), ops.WarpPhotoPlan(B, H, W, "cuda", overlap_zero_fill=True)
+    kept = None
+    for it in range(5):
+        d = make_pairs(B, H, W, "icl", seed=40 + it, device="cuda")
+        a = (d["depth"], d["inv_K"], d["K"], d["T"], d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2))
+        l0, gd0, gs0, gp0 = [t.clone() for t in plain.value_and_grad(*a)]
+        l1, gd1, gs1, gp1 = fast.value_and_grad(*a)
+        torch.cuda.synchronize()
+        if kept is not None:
+            assert kept[0].data_ptr() != gs1.data_ptr()                       # the two buffers alternate
+        assert torch.equal(l0, l1) and torch.equal(gd0, gd1) and torch.equal(gp0, gp1)
+        assert rel_max(gs1.cpu().numpy(), gs0.cpu().numpy()) <= 2e-6         # fp32 atomics: order not fixed
+        kept = (gs1, gs1.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(kept[0], kept[1])                                      # untouched after its call
