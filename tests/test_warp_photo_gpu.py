@@ -356,3 +356,31 @@ def test_plan_overlapped_zero_fill(e2e):
         kept = (gs1, gs1.clone())
     torch.cuda.synchronize()
     assert torch.equal(kept[0], kept[1])                                      # untouched after its call
+
+
+@pytest.mark.parametrize("upstream", ["uniform", "weighted"])
+def test_memory_layouts_agree(e2e, upstream):
+    """Planar (NCHW-contiguous) frames take the generic-stride instances of the kernels, the reference's NCHW views of
+    channels-last memory (train_depth.py:451-453) the interleaved ones: same outputs bit for bit, same gradients."""
+    from e2e_slam_b200.synthetic import make_pairs
+    d = make_pairs(2, 37, 83, "tum", seed=5, rot_deg=3.0, trans=0.1, holes=0.1, device="cuda")
+
+    def run(planar):
+        src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)
+        if planar:
+            src, tgt = src.contiguous(), tgt.contiguous()
+        depth = d["depth"].clone().requires_grad_(True)
+        src = src.detach().requires_grad_(True)
+        T = d["T"].clone().requires_grad_(True)
+        lm, syn, valid, pix = e2e.warp_photometric(depth, d["inv_K"], d["K"], T, src, tgt, "border", True, need_outputs=True)
+        loss = lm.mean() if upstream == "uniform" else (lm * (0.25 + valid)).mean()
+        loss.backward()
+        lmean = e2e.warp_photometric_loss(d["depth"], d["inv_K"], d["K"], d["T"], src.detach(), tgt, "border", True)
+        return [t.detach().clone() for t in (lm, syn, valid, pix, lmean, depth.grad, T.grad, src.grad)]
+
+    a, b = run(False), run(True)
+    for name, x, y in zip(("loss_map", "syn", "valid", "pix", "mean loss"), a[:5], b[:5]):
+        assert torch.equal(x, y), name
+    assert torch.equal(a[5], b[5]), "grad_depth"
+    for name, x, y in zip(("grad_T", "grad_src"), a[6:], b[6:]):
+        assert rel_max(x.cpu().numpy(), y.cpu().numpy()) <= 2e-6, name
