@@ -28,6 +28,10 @@ _SIGNATURES = {
     "e2e_warp_photo_vg": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_scale_by_scalar": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _P]),
     "e2e_u8_to_unit": (_I, [_P, _LL, _P, _P]),
+    "e2e_disp_to_depth_fwd": (_I, [_P, _P, _LL, _P, _P]),
+    "e2e_disp_to_depth_bwd": (_I, [_P, _P, _P, _LL, _P, _P]),
+    "e2e_dual_disparity_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "e2e_dual_disparity_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "e2e_warp_photo_bwd_cond": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_warp_photo_vg_map": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_upstream_uniform": (_I, [_P, _LL, ctypes.c_double, _P, _P]),

@@ -335,6 +335,73 @@ def colors_from_uint8(frames_u8):
     return out
 
 
+class _DispToDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, ratio):
+        f32(disp, "disp")
+        d = disp.contiguous()
+        r = None if ratio is None else f32(ratio, "ratio").detach().reshape(1).contiguous()
+        out = torch.empty_like(d)
+        with torch.cuda.device(d.device):
+            check(lib().e2e_disp_to_depth_fwd(ptr(d), ptr(r), d.numel(), ptr(out), stream_ptr()), "e2e_disp_to_depth_fwd")
+        ctx.save_for_backward(d) if r is None else ctx.save_for_backward(d, r)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        d, r = saved[0], (saved[1] if len(saved) > 1 else None)
+        gd = torch.empty_like(d)
+        with torch.cuda.device(d.device):
+            check(lib().e2e_disp_to_depth_bwd(ptr(d), ptr(r), ptr(f32(g, "grad").contiguous()), d.numel(), ptr(gd), stream_ptr()),
+                  "e2e_disp_to_depth_bwd")
+        return gd, None
+
+
+def disp_to_depth(disp, ratio=None):
+    """depth = 1 / disp, optionally times the median-scaling ratio (a 0-dim device tensor, treated as a constant like the
+    reference's in-place `*= ratio`): online_adaption.py:282, 295-298; train_depth.py:323-340.  One kernel each way."""
+    return _DispToDepth.apply(disp, ratio)
+
+
+def _row_mask(H, device):
+    # l_mask of process_disparity (train_depth.py:231-234) along the rows; torch builds the H values, the kernel applies them
+    return (1.0 - torch.clip(20 * (torch.linspace(0, 1, H) - 0.05), 0, 1)).to(device).contiguous()
+
+
+class _DualDisparity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp2):
+        f32(disp2, "disp")
+        if disp2.dim() != 4 or disp2.shape[0] != 2 or disp2.shape[1] != 1:
+            raise ValueError(f"expected the disparities of a frame and of its mirror image, (2,1,H,W); got {tuple(disp2.shape)}")
+        H, W = disp2.shape[2:]
+        d = disp2.contiguous()
+        m = _row_mask(H, d.device)
+        out = torch.empty(1, 1, H, W, dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            check(lib().e2e_dual_disparity_fwd(ptr(d[0]), ptr(d[1]), ptr(m), H, W, ptr(out), stream_ptr()), "e2e_dual_disparity_fwd")
+        ctx.save_for_backward(m)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (m,) = ctx.saved_tensors
+        H, W = g.shape[2:]
+        gd = torch.empty(2, 1, H, W, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib().e2e_dual_disparity_bwd(ptr(f32(g, "grad").contiguous()), ptr(m), H, W, ptr(gd[0]), ptr(gd[1]), stream_ptr()),
+                  "e2e_dual_disparity_bwd")
+        return gd
+
+
+def dual_disparity(disp2):
+    """process_disparity (train_depth.py:224-237): disp2 (2,1,H,W) = the depth network's disparities for a frame and for its
+    mirror image (the reference feeds `torch.cat([frame, torch.flip(frame, [2])], 0)`, train_depth.py:322-327); the second
+    one is flipped back along W and blended with the first under the row mask.  Returns (1,1,H,W); differentiable."""
+    return _DualDisparity.apply(disp2)
+
+
 def launch_count():
     return _lib.launch_count()
 

@@ -321,6 +321,18 @@ int e2e_icp_point_to_plane(const float *src, long long N, const float *tgt, cons
                            int grad_icp, float lambda_max, float B, float B2, float nu,
                            float *T_out, long long *idx_out, float *errs, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The elementwise passes next to the depth network.
+ *   e2e_disp_to_depth_*    depth = (1 / disp) * ratio: `1 / inputs[("disp", ...)]` and the median rescaling `*= ratio`
+ *                          (online_adaption.py:282, 295-298; train_depth.py:323-340) in one pass; ratio = device scalar, NULL = 1.
+ *   e2e_dual_disparity_*   process_disparity (train_depth.py:224-237): left [H,W] = disparity of the frame, right [H,W] = disparity
+ *                          of its mirror image, row_mask [H] = 1 - clip(20 (linspace(0,1,H) - 0.05), 0, 1).
+ * --------------------------------------------------------------------------------------------- */
+int e2e_disp_to_depth_fwd(const float *disp, const float *ratio, long long n, float *depth, void *stream);
+int e2e_disp_to_depth_bwd(const float *disp, const float *ratio, const float *grad_depth, long long n, float *grad_disp, void *stream);
+int e2e_dual_disparity_fwd(const float *left, const float *right, const float *row_mask, int H, int W, float *out, void *stream);
+int e2e_dual_disparity_bwd(const float *grad_out, const float *row_mask, int H, int W, float *grad_left, float *grad_right, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

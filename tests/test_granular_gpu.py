@@ -216,3 +216,46 @@ def test_colors_from_uint8_is_the_hosts_division():
         assert torch.equal(colors_from_uint8(u.cuda()).cpu(), ref)
     with pytest.raises(TypeError):
         colors_from_uint8(torch.zeros(4).cuda())
+
+
+def test_depth_edge_ops():
+    """`1 / disp` (+ median rescaling) and process_disparity as single kernels, against the reference's
+    torch expressions (online_adaption.py:282, 295-298; train_depth.py:224-237): forward bit for bit, gradients to 1e-6."""
+    from e2e_slam_b200.ops import disp_to_depth, dual_disparity
+    g = torch.Generator().manual_seed(4)
+    disp = torch.rand(2, 1, 57, 91, generator=g) * 9.99 + 0.01                  # DispResNet range (0.01, 10.01)
+    gt = torch.rand(2, 57, 91, 1, generator=g) * 5
+    # reference expressions on the CPU
+    d_ref = disp.clone().requires_grad_(True)
+    depth_ref = 1 / d_ref
+    ratio = (torch.median(gt) / torch.median(depth_ref)).detach()
+    scaled_ref = depth_ref * ratio
+    (scaled_ref * torch.linspace(0.5, 1.5, 91)).sum().backward()
+    d = disp.cuda().requires_grad_(True)
+    assert torch.equal(disp_to_depth(d.detach()).cpu(), depth_ref.detach())
+    out = disp_to_depth(d, ratio.cuda())
+    assert torch.equal(out.detach().cpu(), scaled_ref.detach())
+    (out * torch.linspace(0.5, 1.5, 91).cuda()).sum().backward()
+    assert rel_max(d.grad.cpu().numpy(), d_ref.grad.numpy()) <= 1e-6
+
+    def process_disparity(dd):                                                   # train_depth.py:224-237, device-free
+        left = dd[:1]
+        right = torch.flip(dd[1:], [3])
+        middle = 0.5 * (left + right)
+        h, w = left.shape[2], left.shape[3]
+        l_mesh, _ = torch.meshgrid(torch.linspace(0, 1, h), torch.linspace(0, 1, w), indexing="ij")
+        l_mask = (1.0 - torch.clip(20 * (l_mesh - 0.05), 0, 1)).unsqueeze(0).unsqueeze(0)
+        r_mask = torch.flip(l_mask, [3])
+        return r_mask * left + l_mask * right + (1.0 - l_mask - r_mask) * middle
+
+    p_ref = disp.clone().requires_grad_(True)
+    o_ref = process_disparity(p_ref)
+    w8 = torch.rand(1, 1, 57, 91, generator=g)
+    (o_ref * w8).sum().backward()
+    p = disp.cuda().requires_grad_(True)
+    o = dual_disparity(p)
+    assert o.shape == (1, 1, 57, 91) and torch.equal(o.detach().cpu(), o_ref.detach())
+    (o * w8.cuda()).sum().backward()
+    assert rel_max(p.grad.cpu().numpy(), p_ref.grad.numpy()) <= 1e-6
+    with pytest.raises(ValueError):
+        dual_disparity(disp.cuda()[:1])
