@@ -305,7 +305,7 @@ def test_point_supervision_full_size():
     assert np.abs(ours_d - d ** 2).max() <= 1e-5 * (d ** 2).max()
 
 
-@pytest.mark.parametrize("H,W", [(16, 20), (120, 160), (270, 480)])
+@pytest.mark.parametrize("H,W", [(16, 20), (120, 160), (270, 480), (1080, 1920)])
 def test_sequence_entry_continues_an_existing_map(H, W):
     """e2e_fusion_sequence on frames 0..5 in one call == frames 0..2, then a second call that starts from that map
     (the kernel's prologue converts the caller's [n,3] arrays to its working records): every array bit for bit.
