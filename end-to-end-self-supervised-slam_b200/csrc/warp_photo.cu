@@ -470,6 +470,10 @@ int e2e_warp_photo_fwd(const float *depth, const float *inv_K, const float *K, c
     p.depth = depth; p.inv_K = inv_K; p.K = K; p.T = T;
     if (int rc = set_views(p, src, src_strides, tgt, tgt_strides, 3)) return rc;
     p.syn = syn; p.valid = valid; p.pix = pix; p.loss_map = loss_map;
+    // Default: the value-only instances of the streaming kernel (csrc/warp_photo_fused.cu); E2E_FWD_TILE=1 selects the tile kernel.
+    static const bool use_tile = [] { const char *e = getenv("E2E_FWD_TILE"); return e && e[0] == '1'; }();
+    if (!use_tile && H <= 8189 && W <= 8189 && workspace && workspace_bytes >= stream_workspace_bytes(B, H, W))
+        return launch_stream(p, B, H, W, loss_mean, nullptr, workspace, workspace_bytes, st);
     const dim3 grid = tile_grid(B, H, W, F_TH, F_TW);
     const size_t nct = (size_t)grid.x * grid.y * grid.z;
     if (loss_mean) {
