@@ -13,9 +13,13 @@ adaptation gradients -- over NCCL, overlapped on a side st
 
 Output: ONE JSON line on rank 0 (contract in the task statement), including
   value      device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
-  e2e        same metric through the public Python API with HOST inputs: pinned H2D copies + loss D2H inside
+  e2e        same metric through the public Python API with HOST inputs: pinned H2D copies (8 pipelined chunks) + loss D2H inside
+  e2e_u8_frames   the same leg with the frames crossing PCIe as uint8 (divided by 255 on the device); reported NEXT TO e2e
   roofline   dominant kernel (single-sweep value+gradient kernel) algorithmic bytes / event-timed duration vs measured HBM peak
   cpu_baseline  the reference's CPU path (torch-op oracle) on a bounded sample, on this box's host cores
+  two_kernel_path   forward without autograd, backward for an arbitrary upstream gradient, the autograd loss-map path of patch.fuse()
+  single_pair, c2_refinement_step   configs C1 / C2: latency of one call / one refinement step, eager and as a CUDA graph
+  point_supervision   307 200 live points against a 2 M-point map (grid kNN), loss + gradient
   fusion     secondary metric "points fused/s" of PointFusion over a 60-frame sequence (config C3)
 `--impl reference` times the reference's own CPU implementation of the path (the torch-op restatement in
 oracle/torch_oracle.py, bit-identical to the reference on CPU) with all host threads.
