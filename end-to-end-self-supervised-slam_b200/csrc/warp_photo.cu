@@ -560,6 +560,11 @@ int e2e_ssim_fwd(const float *x, const int64_t x_strides[4], const float *y, con
     if (int rc = fill_common(p, B, C, H, W, 1, 0, 0.f, st)) return rc;
     if (int rc = set_views(p, x, x_strides, y, y_strides, C)) return rc;
     p.ssim = ssim_map; p.loss_map = loss_map;
+    static const bool use_tile = [] { const char *e = getenv("E2E_FWD_TILE"); return e && e[0] == '1'; }();
+    if (C == 3 && !use_tile && H <= 8189 && W <= 8189 && (ssim_map || loss_map)) {      // the streaming kernel, value only
+        const ImgView vx = p.src, vy = p.tgt;
+        if (view_fits_int32(vx, 3, H, W) && view_fits_int32(vy, 3, H, W)) return launch_ssim_stream_bwd(p, B, H, W, st);
+    }
     dim3 grid = tile_grid(B, H, W, F_TH, F_TW);
     if (C == 3) {
         warp_photo_fwd_kernel<MODE_DIRECT, 3, F_TH, F_TW, F_NT, false><<<grid, F_NT, 0, st>>>(p);
