@@ -243,6 +243,8 @@ KNN_MODE = os.environ.get("E2E_KNN", "auto")        # "auto" | "brute" | "grid" 
 
 
 def _use_grid(P1, P2):
+    if P1 > (1 << 24) or P2 >= (1 << 31):           # limits of the grid entry points (far-query list, 32-bit point indices)
+        return False
     if KNN_MODE == "auto":
         return P1 * P2 >= (1 << 24)                  # measured: 19 200 x 75 000 -> grid 0.15 ms, brute force 5.7 ms
     return KNN_MODE == "grid"
