@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(KG_NT) kg_fill_kernel(const float *ref, long l
 
 constexpr int KG_M = 4;               // fine cells per coarse cell and axis (coarse cells only record whether anything is inside)
 constexpr int KG_NEAR_RINGS = 2;      // rings of fine cells searched directly around the query
+#ifndef KG_FAR_MINB
+#define KG_FAR_MINB 6      // latency bound: 48 warps per SM (40 registers, a few outer-loop values spilled) measured faster than 32 or 24
+#endif
 
 // coarse occupancy counts and one bit per FINE cell (2 MB for 2^24 cells: the emptiness test of a fine cell -- 98 % of
 // the cells around a surface are empty -- then stays in cache instead of fetching two words of the 64 MB offset array)
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(KG_NT) kg_query_near_kernel(const float *query
         const float dx_ = xsub(qx, p_.x), dy_ = xsub(qy, p_.y), dz_ = xsub(qz, p_.z);                              \
         const float d2_ = xadd(xadd(xmul(dx_, dx_), xmul(dy_, dy_)), xmul(dz_, dz_));                              \
         const int pi_ = __float_as_int(p_.w);                                                                      \
-        if (d2_ < best || (d2_ == best && pi_ < bi)) { best = d2_; bi = pi_; } /* first minimum in index order */   \
+        if (d2_ <= best) { if (d2_ < best || pi_ < bi) { best = d2_; bi = pi_; } } /* first minimum in index order */ \
     }
     // a query with a non-finite coordinate: every distance is NaN / inf and brute force answers (inf, 0)
     const bool finite = live && isfinite(qx) && isfinite(qy) && isfinite(qz);
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(KG_NT) kg_query_near_kernel(const float *query
 // are dealt out to the lanes, a lane skips a fine cell that is empty or farther than the best known to it, and the lanes'
 // results are merged (minimum of (distance, index)) after every coarse cell that was searched.  The search stops when the
 // best distance lies inside the fully searched cube, so the result is the brute-force result.
-__global__ void __launch_bounds__(KG_NT) kg_query_far_kernel(const float *query, const float *T, const GridParams *gp, const int *start,
+__global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const float *query, const float *T, const GridParams *gp, const int *start,
                                                              const float4 *sorted, const int *coarse, const unsigned *bits,
                                                              float *dist2, long long *idx, const int *far_list, const int *far_count)
 {
@@ -404,25 +407,36 @@ __global__ void __launch_bounds__(KG_NT) kg_query_far_kernel(const float *query,
             }
             const int bx = sx1 - sx0 + 1, by = sy1 - sy0 + 1, bz = sz1 - sz0 + 1;
             const int total = (bx > 0 && by > 0 && bz > 0) ? bx * by * bz : 0;
+            // t -> (x, y, z) of the slab without integer division (three of them per batch were most of the walk's
+            // instructions): quotient by reciprocal multiply, exact for t < 2^21 (total <= 2^18 coarse cells), with a
+            // correction step that costs nothing
+            const float ibx = __frcp_rn((float)max(bx, 1)), iby = __frcp_rn((float)max(by, 1));
             for (int base = 0; base < total; base += 32) {
                 const int t = base + lane;
                 int X = 0, Y = 0, Z = 0;
-                bool hit = false;
+                unsigned key = 0xffffffffu;      // bits of the coarse cell's box distance (>= 0: ordered like the floats); all ones = nothing to search
                 if (t < total) {
-                    X = sx0 + t % bx; Y = sy0 + (t / bx) % by; Z = sz0 + t / (bx * by);
-                    hit = coarse[(Z * my + Y) * mx + X] != 0;
-                    if (hit) {      // the whole coarse cell farther than the best so far (the corners of the outer rings)?
+                    int q1 = (int)(((float)t + 0.5f) * ibx), x = t - q1 * bx;
+                    if (x < 0) { x += bx; q1--; } else if (x >= bx) { x -= bx; q1++; }
+                    int q2 = (int)(((float)q1 + 0.5f) * iby), y = q1 - q2 * by;
+                    if (y < 0) { y += by; q2--; } else if (y >= by) { y -= by; q2++; }
+                    X = sx0 + x; Y = sy0 + y; Z = sz0 + q2;
+                    if (coarse[(Z * my + Y) * mx + X] != 0) {
                         const float hh = hc * (0.5f + slack);
                         const float ex = fmaxf(fabsf(qx - (g.ox + ((float)X + 0.5f) * hc)) - hh, 0.0f);
                         const float ey = fmaxf(fabsf(qy - (g.oy + ((float)Y + 0.5f) * hc)) - hh, 0.0f);
                         const float ez = fmaxf(fabsf(qz - (g.oz + ((float)Z + 0.5f) * hc)) - hh, 0.0f);
-                        hit = !((ex * ex + ey * ey + ez * ez) * 0.9999f > best);
+                        key = __float_as_uint((ex * ex + ey * ey + ez * ez) * 0.9999f);
                     }
                 }
-                unsigned todo = __ballot_sync(0xffffffffu, hit);
-                while (todo) {
-                    const int srcl = __ffs(todo) - 1;
-                    todo &= todo - 1;
+                // nearest occupied coarse cell of the batch first; `best` is the same in every lane here (merged after each
+                // cell), so the batch ends as soon as its nearest unsearched cell is farther than the best distance known --
+                // in the first ring that touches the surface this drops most of the up to 32 candidates unsearched
+                for (;;) {
+                    const unsigned mk = __reduce_min_sync(0xffffffffu, key);
+                    if (mk == 0xffffffffu || __uint_as_float(mk) > best) break;
+                    const int srcl = __ffs(__ballot_sync(0xffffffffu, key == mk)) - 1;
+                    if (lane == srcl) key = 0xffffffffu;
                     const int cX = __shfl_sync(0xffffffffu, X, srcl), cY = __shfl_sync(0xffffffffu, Y, srcl), cZ = __shfl_sync(0xffffffffu, Z, srcl);
                     // the coarse cell's KG_M^3 fine cells, two per lane
                     for (int f = lane; f < KG_M * KG_M * KG_M; f += 32) {
@@ -439,18 +453,14 @@ __global__ void __launch_bounds__(KG_NT) kg_query_far_kernel(const float *query,
                             const float dx = xsub(qx, p.x), dy = xsub(qy, p.y), dz = xsub(qz, p.z);
                             const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
                             const int pi = __float_as_int(p.w);
-                            if (d2 < best || (d2 == best && pi < bi)) { best = d2; bi = pi; }
+                            if (d2 <= best) { if (d2 < best || pi < bi) { best = d2; bi = pi; } }
                         }
                     }
-                }
-                if (__any_sync(0xffffffffu, hit)) {
-                    // merge after every batch of 32 coarse cells: minimum of (distance, index) over the lanes, known to all of them
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                    }
+                    // merge: minimum of (distance, index) over the lanes, known to all of them (distances are >= 0 or +inf:
+                    // their bit patterns order like the values; indices are non-negative)
+                    const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(best));
+                    bi = (int)__reduce_min_sync(0xffffffffu, __float_as_uint(best) == mb ? (unsigned)bi : 0xffffffffu);
+                    best = __uint_as_float(mb);
                 }
             }
             }      // slabs
