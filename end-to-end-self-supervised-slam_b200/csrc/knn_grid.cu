@@ -276,6 +276,48 @@ __global__ void __launch_bounds__(KG_NT) kg_coarse_kernel(long long P2, const Gr
     }
 }
 
+// Tight bounding box of the points of every occupied coarse cell (one warp per cell, after the fill).  A map is a surface:
+// inside a coarse cell it is a thin sheet, and the distance to the sheet's box is a far better bound than the distance to
+// the cell (whose near face can be most of a cell closer than anything in it), so the far search drops most neighbours of
+// the nearest cell unsearched.  Floating-point subtraction is monotone, so |q - p| >= the box distance holds per axis in
+// fp32 exactly; non-finite points (never anyone's nearest) are left out.
+__global__ void __launch_bounds__(KG_NT) kg_coarse_box_kernel(const GridParams *gp, const int *start, const float4 *sorted, const int *coarse,
+                                                              const unsigned *bits, float4 *cbox)
+{
+    const GridParams g = *gp;
+    const int lane = threadIdx.x & 31;
+    const int mx = (g.nx + KG_M - 1) / KG_M, my = (g.ny + KG_M - 1) / KG_M, mz = (g.nz + KG_M - 1) / KG_M;
+    const long long total = (long long)mx * my * mz;
+    for (long long cc = (long long)blockIdx.x * (KG_NT / 32) + (threadIdx.x >> 5); cc < total; cc += (long long)gridDim.x * (KG_NT / 32)) {
+        if (coarse[cc] == 0) continue;
+        const int cX = (int)(cc % mx), cY = (int)((cc / mx) % my), cZ = (int)(cc / ((long long)mx * my));
+        float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+        for (int f = lane; f < KG_M * KG_M * KG_M; f += 32) {
+            const int x = cX * KG_M + (f % KG_M), y = cY * KG_M + (f / KG_M) % KG_M, z = cZ * KG_M + f / (KG_M * KG_M);
+            if (x >= g.nx || y >= g.ny || z >= g.nz) continue;
+            const int c = (z * g.ny + y) * g.nx + x;
+            if (!((bits[c >> 5] >> (c & 31)) & 1u)) continue;
+            for (int j = start[c], e = start[c + 1]; j < e; j++) {
+                const float4 p = sorted[j];
+                if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+                    lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
+                    hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+            lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+            hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+        }
+        if (lane == 0) {
+            cbox[2 * cc] = make_float4(lx, ly, lz, 0.0f);
+            cbox[2 * cc + 1] = make_float4(hx, hy, hz, 0.0f);
+        }
+    }
+}
+
 // Query, phase 1 -- one thread per query: the fine cells within KG_NEAR_RINGS of the query's cell, ring by ring.  A query
 // this close to the cloud (the usual case) is decided here; the others are appended to `far_list` with what they have found.
 __global__ void __launch_bounds__(KG_NT) kg_query_near_kernel(const float *query, const float *T, long long P1, const GridParams *gp,
@@ -356,7 +398,7 @@ __global__ void __launch_bounds__(KG_NT) kg_query_near_kernel(const float *query
 // results are merged (minimum of (distance, index)) after every coarse cell that was searched.  The search stops when the
 // best distance lies inside the fully searched cube, so the result is the brute-force result.
 __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const float *query, const float *T, const GridParams *gp, const int *start,
-                                                             const float4 *sorted, const int *coarse, const unsigned *bits,
+                                                             const float4 *sorted, const int *coarse, const float4 *cbox, const unsigned *bits,
                                                              float *dist2, long long *idx, const int *far_list, const int *far_count)
 {
     const GridParams g = *gp;
@@ -384,7 +426,8 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
         const int qX = cdiv(cx), qY = cdiv(cy), qZ = cdiv(cz);
         const float hc = g.h * (float)KG_M, half = g.h * (0.5f + slack);
         // rings before the first one that can touch the grid hold nothing
-        int r = max(max(max(-qX, qX - (mx - 1)), max(-qY, qY - (my - 1))), max(max(-qZ, qZ - (mz - 1)), 0));
+        // (and the walk starts with the 27 cells of box(1) as ONE batch: nearest first works best on a whole neighbourhood)
+        int r = max(max(max(-qX, qX - (mx - 1)), max(-qY, qY - (my - 1))), max(max(-qZ, qZ - (mz - 1)), 1));
         int pX0 = 0, pX1 = -1, pY0 = 0, pY1 = -1, pZ0 = 0, pZ1 = -1;      // the part of the grid searched so far (empty)
         for (;; r++) {
             // the coarse cells of ring r inside the grid = box(r) minus box(r - 1), enumerated as up to six slabs (a query far
@@ -393,9 +436,12 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
             const int X0 = max(qX - r, 0), X1 = min(qX + r, mx - 1), Y0 = max(qY - r, 0), Y1 = min(qY + r, my - 1),
                       Z0 = max(qZ - r, 0), Z1 = min(qZ + r, mz - 1);
             const bool fresh = pX1 < pX0 || pY1 < pY0 || pZ1 < pZ0;
-            for (int slab = 0; slab < (fresh ? 1 : 6); slab++) {
+            // small rings (box(2) = 125 cells = 4 batches): the whole box, the lanes skipping what box(r - 1) covered -- six
+            // thin slabs would be six mostly empty batches
+            const bool whole = fresh || r <= 2;
+            for (int slab = 0; slab < (whole ? 1 : 6); slab++) {
             int sx0 = X0, sx1 = X1, sy0 = Y0, sy1 = Y1, sz0 = Z0, sz1 = Z1;
-            if (!fresh) {
+            if (!whole) {
                 if (slab == 0) sx1 = pX0 - 1;
                 if (slab == 1) sx0 = pX1 + 1;
                 if (slab >= 2) { sx0 = pX0; sx1 = pX1; }
@@ -407,25 +453,30 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
             }
             const int bx = sx1 - sx0 + 1, by = sy1 - sy0 + 1, bz = sz1 - sz0 + 1;
             const int total = (bx > 0 && by > 0 && bz > 0) ? bx * by * bz : 0;
+            if (total == 0) continue;
             // t -> (x, y, z) of the slab without integer division (three of them per batch were most of the walk's
-            // instructions): quotient by reciprocal multiply, exact for t < 2^21 (total <= 2^18 coarse cells), with a
-            // correction step that costs nothing
-            const float ibx = __frcp_rn((float)max(bx, 1)), iby = __frcp_rn((float)max(by, 1));
+            // instructions): quotient by (approximate) reciprocal multiply, off by at most two for t < 2^22 (there are
+            // at most 2^21.7 coarse cells), put right by the correction loops
+            const float ibx = __fdividef(1.0f, (float)bx), iby = __fdividef(1.0f, (float)by);
             for (int base = 0; base < total; base += 32) {
                 const int t = base + lane;
                 int X = 0, Y = 0, Z = 0;
                 unsigned key = 0xffffffffu;      // bits of the coarse cell's box distance (>= 0: ordered like the floats); all ones = nothing to search
                 if (t < total) {
                     int q1 = (int)(((float)t + 0.5f) * ibx), x = t - q1 * bx;
-                    if (x < 0) { x += bx; q1--; } else if (x >= bx) { x -= bx; q1++; }
+                    while (x < 0) { x += bx; q1--; }
+                    while (x >= bx) { x -= bx; q1++; }
                     int q2 = (int)(((float)q1 + 0.5f) * iby), y = q1 - q2 * by;
-                    if (y < 0) { y += by; q2--; } else if (y >= by) { y -= by; q2++; }
+                    while (y < 0) { y += by; q2--; }
+                    while (y >= by) { y -= by; q2++; }
                     X = sx0 + x; Y = sy0 + y; Z = sz0 + q2;
-                    if (coarse[(Z * my + Y) * mx + X] != 0) {
-                        const float hh = hc * (0.5f + slack);
-                        const float ex = fmaxf(fabsf(qx - (g.ox + ((float)X + 0.5f) * hc)) - hh, 0.0f);
-                        const float ey = fmaxf(fabsf(qy - (g.oy + ((float)Y + 0.5f) * hc)) - hh, 0.0f);
-                        const float ez = fmaxf(fabsf(qz - (g.oz + ((float)Z + 0.5f) * hc)) - hh, 0.0f);
+                    const int cc = (Z * my + Y) * mx + X;
+                    const bool seen = whole && !fresh && X >= pX0 && X <= pX1 && Y >= pY0 && Y <= pY1 && Z >= pZ0 && Z <= pZ1;
+                    if (!seen && coarse[cc] != 0) {      // distance to the tight box of the cell's points (kg_coarse_box_kernel)
+                        const float4 lo = cbox[2 * cc], hi = cbox[2 * cc + 1];
+                        const float ex = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
+                        const float ey = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
+                        const float ez = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
                         key = __float_as_uint((ex * ex + ey * ey + ez * ez) * 0.9999f);
                     }
                 }
@@ -498,7 +549,7 @@ size_t e2e_knn1_grid_workspace_bytes(long long P2)
 {
     if (P2 < 0) P2 = 0;
     return 2 * kg_a256(KG_PADDED * 4) + kg_a256((size_t)P2 * 4) + kg_a256((size_t)P2 * 16) + kg_a256(sizeof(GridParams)) +
-           kg_a256((KG_PADDED / 4096) * 4) + kg_a256(KG_COARSE * 4) + kg_a256(KG_PADDED / 8) + 256 + 256 + 256;
+           kg_a256((KG_PADDED / 4096) * 4) + kg_a256(KG_COARSE * 4) + kg_a256(KG_PADDED / 8) + 256 + 256 + 256 + kg_a256(KG_COARSE * 32);
 }
 
 // Build the grid over `ref` into `workspace` (e2e_knn1_grid_workspace_bytes(P2)); the grid stays valid for any number of
@@ -518,7 +569,8 @@ int e2e_knn1_grid_build(const float *ref, long long P2, void *workspace, size_t 
     int *chunk_sum = (int *)w;          w += kg_a256((KG_PADDED / 4096) * 4);
     int *coarse = (int *)w;             w += kg_a256(KG_COARSE * 4);
     unsigned *bits = (unsigned *)w;     w += kg_a256(KG_PADDED / 8);
-    unsigned *bb = (unsigned *)w;
+    unsigned *bb = (unsigned *)w;       w += 3 * 256;      // bbox words, far-query counter
+    float4 *cbox = (float4 *)w;         // written for occupied coarse cells only, read only where coarse != 0: no clear
     // bbox accumulators: minima start at all ones, maxima at zero (ordered encoding); the histogram's padding stays zero
     if (cudaMemsetAsync(bb, 0xff, 12, st) != cudaSuccess || cudaMemsetAsync(bb + 3, 0x00, 12, st) != cudaSuccess ||
         cudaMemsetAsync(start, 0, KG_PADDED * 4, st) != cudaSuccess || cudaMemsetAsync(coarse, 0, KG_COARSE * 4 , st) != cudaSuccess ||
@@ -537,7 +589,8 @@ int e2e_knn1_grid_build(const float *ref, long long P2, void *workspace, size_t 
     kg_scan3_kernel<<<chunks, 1024, 0, st>>>(start, chunk_sum, cursor, gp);
     kg_fill_kernel<<<nb, KG_NT, 0, st>>>(ref, P2, cell_of, cursor, sorted);
     kg_coarse_kernel<<<nb, KG_NT, 0, st>>>(P2, gp, cell_of, coarse, bits);
-    count_launch(2 + 3 * KG_PASSES - 1 + 5);
+    kg_coarse_box_kernel<<<kNumSMs * 16, KG_NT, 0, st>>>(gp, start, sorted, coarse, bits, cbox);
+    count_launch(2 + 3 * KG_PASSES - 1 + 6);
     return finish_launch("knn1_grid_build");
 }
 
@@ -553,6 +606,7 @@ int e2e_knn1_grid_query(const float *query, const float *transform, long long P1
     const int *coarse = (const int *)w;             w += kg_a256(KG_COARSE * 4);
     const unsigned *bits = (const unsigned *)w;
     int *far_count = (int *)(const_cast<unsigned char *>(w) + kg_a256(KG_PADDED / 8) + 256);      // after the bitmap and the bbox words
+    const float4 *cbox = (const float4 *)(w + kg_a256(KG_PADDED / 8) + 3 * 256);
     const long long qb = (P1 + KG_NT - 1) / KG_NT;
     E2E_REQUIRE(qb < (1ll << 31) && P1 < (1ll << 31), "knn1_grid: too many query points");
     // the list of far queries borrows the first P1 ints of the cursor array (dead after the build: 2^24 ints)
@@ -562,7 +616,7 @@ int e2e_knn1_grid_query(const float *query, const float *transform, long long P1
     kg_query_near_kernel<<<(unsigned)qb, KG_NT, 0, st>>>(query, transform, P1, gp, start, sorted, bits, dist2, idx, far_list, far_count);
     long long fb = (P1 + KG_NT / 32 - 1) / (KG_NT / 32);
     if (fb > kNumSMs * 32) fb = kNumSMs * 32;
-    kg_query_far_kernel<<<(unsigned)fb, KG_NT, 0, st>>>(query, transform, gp, start, sorted, coarse, bits, dist2, idx, far_list, far_count);
+    kg_query_far_kernel<<<(unsigned)fb, KG_NT, 0, st>>>(query, transform, gp, start, sorted, coarse, cbox, bits, dist2, idx, far_list, far_count);
     count_launch(2);
     return finish_launch("knn1_grid_query");
 }
