@@ -455,20 +455,25 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
             const int total = (bx > 0 && by > 0 && bz > 0) ? bx * by * bz : 0;
             if (total == 0) continue;
             // t -> (x, y, z) of the slab without integer division (three of them per batch were most of the walk's
-            // instructions): quotient by (approximate) reciprocal multiply, off by at most two for t < 2^22 (there are
-            // at most 2^21.7 coarse cells), put right by the correction loops
+            // instructions): quotient = floor((t + 0.5) * rcp(b)).  (t + 0.5) / b is at least 0.5 / b away from an integer and the
+            // computed product is within (t + 0.5) / b * 1.3 * 2^-22 of it (reciprocal to 2 ulp, one rounding), so the floor is exact
+            // for t < 1.6 M; a slab of more than 2^20 cells (a query far outside a huge flat grid) takes the integer division
             const float ibx = __fdividef(1.0f, (float)bx), iby = __fdividef(1.0f, (float)by);
+            const bool exact_rcp = total <= (1 << 20);
             for (int base = 0; base < total; base += 32) {
                 const int t = base + lane;
                 int X = 0, Y = 0, Z = 0;
                 unsigned key = 0xffffffffu;      // bits of the coarse cell's box distance (>= 0: ordered like the floats); all ones = nothing to search
                 if (t < total) {
-                    int q1 = (int)(((float)t + 0.5f) * ibx), x = t - q1 * bx;
-                    while (x < 0) { x += bx; q1--; }
-                    while (x >= bx) { x -= bx; q1++; }
-                    int q2 = (int)(((float)q1 + 0.5f) * iby), y = q1 - q2 * by;
-                    while (y < 0) { y += by; q2--; }
-                    while (y >= by) { y -= by; q2++; }
+                    int q1, q2;
+                    if (exact_rcp) {
+                        q1 = (int)(((float)t + 0.5f) * ibx);
+                        q2 = (int)(((float)q1 + 0.5f) * iby);
+                    } else {
+                        q1 = t / bx;
+                        q2 = q1 / by;
+                    }
+                    const int x = t - q1 * bx, y = q1 - q2 * by;
                     X = sx0 + x; Y = sy0 + y; Z = sz0 + q2;
                     const int cc = (Z * my + Y) * mx + X;
                     const bool seen = whole && !fresh && X >= pX0 && X <= pX1 && Y >= pY0 && Y <= pY1 && Z >= pZ0 && Z <= pZ1;
