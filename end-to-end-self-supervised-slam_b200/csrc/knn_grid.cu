@@ -256,7 +256,12 @@ __global__ void __launch_bounds__(KG_NT) kg_fill_kernel(const float *ref, long l
     }
 }
 
-constexpr int KG_M = 4;               // fine cells per coarse cell and axis (coarse cells only record whether anything is inside)
+#ifndef KG_M_VAL
+#define KG_M_VAL 4
+#endif
+constexpr int KG_M = KG_M_VAL;               // fine cells per coarse cell and axis (coarse cells only record whether anything is inside)
+// measured (307 200 queries ~7 cm off a 2 M-point surface / config C2 step): M = 2: 2.57 / 4.67 ms, 3: 1.85 / 2.56, 4: 1.63 / 1.95,
+// 6: 1.82 / 2.30, 8: 1.95 / 2.56 -- smaller cells lengthen the ring walk, larger ones loosen the boxes and the search per cell
 constexpr int KG_NEAR_RINGS = 2;      // rings of fine cells searched directly around the query
 #ifndef KG_FAR_MINB
 #define KG_FAR_MINB 6      // latency bound: 48 warps per SM (40 registers, a few outer-loop values spilled) measured faster than 32 or 24
