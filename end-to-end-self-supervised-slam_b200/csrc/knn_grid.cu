@@ -345,43 +345,54 @@ __global__ void __launch_bounds__(KG_NT) kg_query_near_kernel(const float *query
     }
     float best = INFINITY;
     int bi = 0;
-#define KG_SCAN_CELL(c)                                                                                           \
-    if ((bits[(c) >> 5] >> ((c) & 31)) & 1u)                                                                       \
-    for (int j_ = start[(c)], e_ = start[(c) + 1]; j_ < e_; j_++) {                                                \
-        const float4 p_ = sorted[j_];                                                                              \
-        const float dx_ = xsub(qx, p_.x), dy_ = xsub(qy, p_.y), dz_ = xsub(qz, p_.z);                              \
-        const float d2_ = xadd(xadd(xmul(dx_, dx_), xmul(dy_, dy_)), xmul(dz_, dz_));                              \
-        const int pi_ = __float_as_int(p_.w);                                                                      \
-        if (d2_ <= best) { if (d2_ < best || pi_ < bi) { best = d2_; bi = pi_; } } /* first minimum in index order */ \
-    }
     // a query with a non-finite coordinate: every distance is NaN / inf and brute force answers (inf, 0)
     const bool finite = live && isfinite(qx) && isfinite(qy) && isfinite(qz);
     bool decided = !finite;
     if (finite) {
         const int cx = cell_coord(qx, g.ox, g.inv_h), cy = cell_coord(qy, g.oy, g.inv_h), cz = cell_coord(qz, g.oz, g.inv_h);
         const float slack = 0.01f + 4e-7f * (float)max(max(g.nx, g.ny), g.nz);      // cells: rounding of the cell coordinates
-        for (int r = 0; r <= KG_NEAR_RINGS && !decided; r++) {
-            const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
-            const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
-            const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
-            for (int z = z0; z <= z1; z++) {
-                const bool zface = (z == cz - r) || (z == cz + r);
-                for (int y = y0; y <= y1; y++) {
-                    const int row = (z * g.ny + y) * g.nx;
-                    if (zface || y == cy - r || y == cy + r) {          // a face of the cube: the whole row belongs to ring r
-                        for (int x = x0; x <= x1; x++) KG_SCAN_CELL(row + x)
-                    } else {                                            // inside: only the two x faces
-                        if (cx - r >= 0 && cx - r <= g.nx - 1) KG_SCAN_CELL(row + cx - r)
-                        if (r > 0 && cx + r >= 0 && cx + r <= g.nx - 1) KG_SCAN_CELL(row + cx + r)
+        // The occupancy bits of an x-row of cells are adjacent in the bitmap: one funnel shift fetches the row, and only occupied
+        // cells are visited (a loop over all 27 / 125 cells with a test per cell leaves most lanes idle while a few scan points).
+        // Rings 0-1 first (the 3 x 3 rows of three cells), then, if the nearest point is not yet proven, ring 2 (5 x 5 rows of
+        // five cells less the part already searched).
+#pragma unroll 1
+        for (int R = 1; R <= KG_NEAR_RINGS && !decided; R++) {
+            const int xlo = max(cx - R, 0), xhi = min(cx + R, g.nx - 1);
+            if (xlo <= xhi) {
+                const unsigned xmask = (2u << (xhi - xlo)) - 1u;                    // xhi - xlo <= 4
+                // the cells of this row that rings < R covered: x in [cx - R + 1, cx + R - 1], if the row itself was covered
+                const int ilo = max(cx - R + 1, xlo), ihi = min(cx + R - 1, xhi);
+                const unsigned inner = (R > 1 && ilo <= ihi) ? (((2u << (ihi - ilo)) - 1u) << (ilo - xlo)) : 0u;
+#pragma unroll 1
+                for (int dz = -R; dz <= R; dz++) {
+                    const int z = cz + dz;
+                    if (z < 0 || z >= g.nz) continue;
+#pragma unroll 1
+                    for (int dy = -R; dy <= R; dy++) {
+                        const int y = cy + dy;
+                        if (y < 0 || y >= g.ny) continue;
+                        const int c0 = (z * g.ny + y) * g.nx + xlo;
+                        unsigned m = __funnelshift_r(bits[c0 >> 5], bits[(c0 >> 5) + 1], c0 & 31) & xmask;
+                        if (abs(dz) < R && abs(dy) < R) m &= ~inner;
+                        while (m) {
+                            const int c = c0 + __ffs(m) - 1;
+                            m &= m - 1;
+                            for (int j = start[c], e = start[c + 1]; j < e; j++) {
+                                const float4 p = sorted[j];
+                                const float dx = xsub(qx, p.x), dy2 = xsub(qy, p.y), dz2 = xsub(qz, p.z);
+                                const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy2, dy2)), xmul(dz2, dz2));
+                                const int pi = __float_as_int(p.w);
+                                if (d2 <= best) { if (d2 < best || pi < bi) { best = d2; bi = pi; } }      // first minimum in index order
+                            }
+                        }
                     }
                 }
             }
-            // every point within Chebyshev cell distance r has been seen, i.e. every point closer than r*h (less the slack)
-            const float reach = ((float)r - slack) * g.h;
-            decided = reach > 0.0f && best <= reach * reach;
+            // every point within Chebyshev cell distance R has been seen, i.e. every point closer than R*h (less the slack)
+            const float reach = ((float)R - slack) * g.h;
+            decided = best <= reach * reach;
         }
     }
-#undef KG_SCAN_CELL
     if (live) {
         dist2[i] = best;
         idx[i] = (long long)bi;
