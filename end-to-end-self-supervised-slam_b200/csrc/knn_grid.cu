@@ -63,10 +63,22 @@ __global__ void __launch_bounds__(KG_NT) kg_bbox_kernel(const float *ref, long l
             lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(bb + k, ordered_bits(lo[k]));
-            atomicMax(bb + 3 + k, ordered_bits(hi[k]));
-        }
+    }
+    // one pair of atomics per axis and CTA (per warp they were most of this kernel's time: ~19 k atomics on each of six words)
+    __shared__ float s_lo[3][KG_NT / 32], s_hi[3][KG_NT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { s_lo[k][warp] = lo[k]; s_hi[k][warp] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        float l = s_lo[k][0], h = s_hi[k][0];
+#pragma unroll
+        for (int w = 1; w < KG_NT / 32; w++) { l = fminf(l, s_lo[k][w]); h = fmaxf(h, s_hi[k][w]); }
+        atomicMin(bb + k, ordered_bits(l));
+        atomicMax(bb + 3 + k, ordered_bits(h));
     }
 }
 
@@ -598,7 +610,7 @@ int e2e_knn1_grid_build(const float *ref, long long P2, void *workspace, size_t 
         cudaMemsetAsync(bits, 0, KG_PADDED / 8, st) != cudaSuccess)
         return finish_launch("knn1_grid: memset");
     const int nb = kg_blocks(P2), chunks = (int)(KG_PADDED / 4096);
-    kg_bbox_kernel<<<nb, KG_NT, 0, st>>>(ref, P2, bb);
+    kg_bbox_kernel<<<nb < kNumSMs * 8 ? nb : kNumSMs * 8, KG_NT, 0, st>>>(ref, P2, bb);
     kg_params_kernel<<<1, 1, 0, st>>>(bb, P2, gp);
     for (int pass = 0; pass < KG_PASSES; pass++) {
         if (pass) kg_clear_kernel<<<kNumSMs * 8, KG_NT, 0, st>>>((int4 *)start, (int)(KG_PADDED / 4), gp);
