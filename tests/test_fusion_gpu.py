@@ -364,7 +364,7 @@ def _knn_both(q, r, T=None):
 
 
 @pytest.mark.parametrize("case", ["uniform", "surface", "clustered", "duplicates", "far_queries", "all_far", "off_surface", "line", "single",
-                                  "nonfinite"])
+                                  "nonfinite", "slanted_far", "box_edges"])
 def test_grid_knn_equals_brute_force(case):
     """The uniform-grid kernel must return the brute-force kernel's answer bit for bit (same distance arithmetic, lowest
     index among exact ties) whatever the shape of the clouds."""
@@ -402,6 +402,16 @@ def test_grid_knn_equals_brute_force(case):
         q = torch.zeros(4000, 3, device="cuda"); q[:, 0] = rnd(4000) * 12 - 1; q[:, 1] = 0.01 * rnd(4000)
     elif case == "single":
         r, q = rnd(1, 3), rnd(100, 3) * 5
+    elif case == "slanted_far":                 # a steep, thick sheet and queries 0-60 cm off it: long ring walks, tight coarse boxes
+        uv = rnd(300000, 2) * 4 - 2
+        r = torch.stack([uv[:, 0], uv[:, 1], 3.0 + 0.9 * uv[:, 0] - 0.6 * uv[:, 1]], 1) + 0.01 * (rnd(300000, 3) - 0.5)
+        q = r[torch.randperm(300000, device="cuda", generator=g)[:20000]].clone()
+        q += 0.6 * (rnd(20000, 1) ** 2) * torch.nn.functional.normalize(torch.randn(20000, 3, generator=g, device="cuda"), dim=1)
+    elif case == "box_edges":                   # queries on and just outside the faces, edges and corners of the reference box
+        r = rnd(80000, 3)
+        side = torch.randint(0, 3, (12000, 3), device="cuda", generator=g).float() * 0.5      # 0, 0.5 or 1 per axis
+        q = side + 0.03 * (rnd(12000, 3) - 0.5)
+        q[::7] = side[::7]                                                                     # exactly on the faces
     else:                                       # NaN / inf on either side never match; all-NaN queries answer (inf, 0) like brute force
         r = rnd(5000, 3); r[17] = float("nan"); r[99, 1] = float("inf")
         q = rnd(600, 3); q[3, 2] = float("nan"); q[40] = float("inf")
