@@ -1,15 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the B200 differentiable-geometry hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch_cuda] [--scaling strong|weak]
 
 Metric (BASELINE.json): warped px/s of the fused inverse warp + SSIM/L1 photometric loss, forward +
 backward (gradients to depth, pose and source image).  Workload = BASELINE config "C4 batched-256":
 256 synthetic ICL-shaped 480x640 key-frame pairs per GPU, S = 1 source frame, border padding,
 photometric mask on.  One step = one forward + backward pass over the batch.
-Multi-GPU: pairs are independent, every rank owns its own 256 pairs (weak scaling, no data-path
-collective); at N > 1 each step also all-reduces a 57.3 MB fp32 bucket -- the size of the depth network's
-adaptation gradients -- over NCCL, overlapped on a side stream.
+Multi-GPU (BASELINE config C4 as written): the 256 pairs are SHARDED, rank r owns pairs r::G (256/G per rank, strong
+scaling, no data-path collective); each step also all-reduces a 57.3 MB fp32 bucket -- the size of the depth network's
+adaptation gradients -- over NCCL, overlapped on a side stream.  `--scaling weak` keeps 256 pairs
+per rank instead; at N > 1 the line carries the other mode's numbers too (`weak_scaling` / `strong_scaling`).
 
 Output: ONE JSON line on rank 0 (contract in the task statement), including
   value      device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
@@ -21,8 +22,10 @@ Output: ONE JSON line on rank 0 (contract in the task statement), including
   single_pair, c2_refinement_step   configs C1 / C2: latency of one call / one refinement step, eager and as a CUDA graph
   point_supervision   307 200 live points against a 2 M-point map (grid kNN), loss + gradient
   fusion     secondary metric "points fused/s" of PointFusion over a 60-frame sequence (config C3)
+  torch_cuda_baseline   the reference's own UNFUSED call sequence as ATen CUDA kernels on the same B200 (the honest GPU baseline)
 `--impl reference` times the reference's own CPU implementation of the path (the torch-op restatement in
-oracle/torch_oracle.py, bit-identical to the reference on CPU) with all host threads.
+oracle/torch_oracle.py, bit-identical to the reference on CPU) with all host threads, on all 256 pairs per step.
+`--impl torch_cuda` times the unfused torch-CUDA call sequence alone.
 """
 import argparse
 import json
@@ -114,21 +117,31 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_px_per_s(pairs, reps, warm, threads):
-    """The reference's CPU path (torch-op restatement, same ATen kernels the reference runs) fwd+bwd."""
+CPU_CHUNK = 16                          # pairs per CPU call: 256 pairs = 16 chunks (keeps the CPU leg's working set ~1 GB)
+WORKLOAD = ("C4 batched-256: 256 ICL-shaped 480x640 key-frame pairs sharded over the GPUs, S=1, fused warp+SSIM/L1 loss + gradients "
+            "(to depth, source image, pose)")
+
+
+def base_config(world, scaling, pairs_per_gpu):
+    """`config` of the JSON line; identical for the repo arm and the reference arms (same workload, same shapes)."""
+    return {"workload": WORKLOAD, "global_pairs": pairs_per_gpu * world, "height": H, "width": W, "source_frames": 1,
+            "padding_mode": "border", "photometric_mask": True, "scaling": scaling}
+
+
+def cpu_reference_step(pairs, threads):
+    """One pass of the reference's CPU path (torch-op restatement, same ATen kernels the reference runs) over `pairs` pairs of the
+    workload, fwd+bwd, in chunks of CPU_CHUNK pairs.  Returns seconds."""
     from e2e_slam_b200.synthetic import make_pairs
     from oracle import torch_oracle
     torch.set_num_threads(threads)
-    d = make_pairs(pairs, H, W, "icl", seed=1234)
-    src, tgt = d["colors"][:, 0], d["colors"][:, 1]
-    times = []
-    for i in range(warm + reps):
+    t = 0.0
+    for s0 in range(0, pairs, CPU_CHUNK):
+        d = make_pairs(min(CPU_CHUNK, pairs - s0), H, W, "icl", seed=1234 + s0)      # generation is outside the timed region
+        src, tgt = d["colors"][:, 0], d["colors"][:, 1]
         t0 = time.perf_counter()
         torch_oracle.fwd_bwd(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt, "border", True)
-        dt = time.perf_counter() - t0
-        if i >= warm:
-            times.append(dt)
-    return pairs * H * W / min(times), pairs * H * W / (sum(times) / len(times)), times
+        t += time.perf_counter() - t0
+    return t
 
 
 def run_reference(args):
@@ -137,30 +150,113 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     pairs = args.cpu_pairs
-    from e2e_slam_b200.synthetic import make_pairs
-    from oracle import torch_oracle
-    torch.set_num_threads(threads)
-    d = make_pairs(pairs, H, W, "icl", seed=1234)
-    src, tgt = d["colors"][:, 0], d["colors"][:, 1]
-    step = lambda: torch_oracle.fwd_bwd(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt, "border", True)
     for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
+        cpu_reference_step(min(pairs, CPU_CHUNK), threads)       # warm-up: one chunk (page-in, thread pool) per step
+    dt = 0.0
     for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
+        dt += cpu_reference_step(pairs, threads)
     v = pairs * H * W * args.steps / dt
-    sample = f"{pairs} of the workload's 256 pairs per step, 480x640, fwd+bwd (grads to depth, source, pose), fp32, {threads} torch threads"
+    sample = (f"all {pairs} pairs of the workload per step in chunks of {CPU_CHUNK}, 480x640, fwd+bwd (grads to depth, source, pose), fp32, "
+              f"{threads} torch threads; warm-up steps run one chunk each")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "px/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling or "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4 batched-256 (bounded sample on CPU)", "pairs_per_step": pairs, "height": H, "width": W,
-                   "source_frames": 1, "padding_mode": "border", "photometric_mask": True},
+        "config": base_config(1, args.scaling or "strong", pairs),
         "cpu_baseline": {"value": v, "unit": "px/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ---- the reference's own call sequence as plain torch ops on the GPU (train_depth.py:545-613, 707-727, 657): the unfused ATen-CUDA
+# baseline the fused kernels have to beat.  Written out here (not imported from oracle/, which is CPU test infrastructure). ----------
+def torch_cuda_fwd_bwd(depth, inv_K, K, T, src_cl, tgt_cl):
+    import torch.nn.functional as F
+    B, _, Hh, Ww = depth.shape
+    dev = depth.device
+    depth = depth.detach().requires_grad_(True)
+    T = T.detach().requires_grad_(True)
+    src_cl = src_cl.detach().requires_grad_(True)
+    src, tgt = src_cl.permute(0, 3, 1, 2), tgt_cl.permute(0, 3, 1, 2)                  # train_depth.py:451-453
+    ys, xs = torch.meshgrid(torch.arange(Hh, dtype=torch.float32, device=dev), torch.arange(Ww, dtype=torch.float32, device=dev), indexing="ij")
+    grid = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(Hh * Ww, device=dev)], 0).unsqueeze(0).expand(B, 3, Hh * Ww)
+    pts = depth.view(B, 1, -1) * torch.matmul(inv_K[:, :3, :3], grid)                     # view_synthesis.py:36-38
+    pts = torch.cat([pts, torch.ones(B, 1, Hh * Ww, device=dev)], 1)
+    P = torch.matmul(K, T)[:, :3, :]                                                      # :57
+    c = torch.matmul(P, pts)
+    pix = c[:, :2, :] / (c[:, 2, :].unsqueeze(1) + 1e-7)
+    pix = pix.view(B, 2, Hh, Ww).permute(0, 2, 3, 1)
+    pix = torch.stack([pix[..., 0] / (Ww - 1), pix[..., 1] / (Hh - 1)], -1)
+    pix = (pix - 0.5) * 2
+    valid = (pix.abs().max(dim=-1)[0] <= 1).unsqueeze(1).float()
+    syn = F.grid_sample(src, pix, padding_mode="border", align_corners=False)             # train_depth.py:587-590
+    x, y = syn * valid, tgt * valid                                                       # :714-715
+    xp, yp = F.pad(x, (1, 1, 1, 1), mode="reflect"), F.pad(y, (1, 1, 1, 1), mode="reflect")     # losses.py:23-37
+    mu_x, mu_y = F.avg_pool2d(xp, 3, 1), F.avg_pool2d(yp, 3, 1)
+    sig_x = F.avg_pool2d(xp ** 2, 3, 1) - mu_x ** 2
+    sig_y = F.avg_pool2d(yp ** 2, 3, 1) - mu_y ** 2
+    sig_xy = F.avg_pool2d(xp * yp, 3, 1) - mu_x * mu_y
+    n = (2 * mu_x * mu_y + 1e-4) * (2 * sig_xy + 9e-4)
+    dn = (mu_x ** 2 + mu_y ** 2 + 1e-4) * (sig_x + sig_y + 9e-4)
+    ssim = torch.clamp((1 - n / dn) / 2, 0, 1)
+    lm = 0.85 * ssim.mean(1, True) + 0.15 * torch.abs(y - x).mean(1, True)                # losses.py:111-115
+    loss = lm.mean()                                                                       # train_depth.py:657
+    loss.backward()
+    return loss.detach()
+
+
+def torch_cuda_baseline(dev, pairs, steps, warmup, chunk=32):
+    """px/s of the unfused torch-CUDA call sequence over `pairs` pairs per step (chunks of `chunk`: its intermediates need ~0.2 GB
+    per pair), CUDA-event timed."""
+    from e2e_slam_b200.synthetic import make_pairs
+    chunks = [make_pairs(min(chunk, pairs - s0), H, W, "icl", seed=1000 + s0, device=dev) for s0 in range(0, pairs, chunk)]
+
+    def step():
+        for d in chunks:
+            torch_cuda_fwd_bwd(d["depth"], d["inv_K"], d["K"], d["T"], d["colors"][:, 0], d["colors"][:, 1])
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": pairs * H * W / (ms * 1e-3), "unit": "px/s", "ms_per_step": ms, "pairs_per_step": pairs, "chunk_pairs": chunk,
+            "kind": "the reference's call sequence (BackprojectDepth -> Project3D -> F.grid_sample -> mask -> SSIM -> photometric_loss -> "
+                    ".mean() -> backward) as plain torch ops on the same GPU, fp32, eager",
+            "reference_lines": "train_depth.py:545-613, 707-727, 657"}
+
+
+def run_torch_cuda(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = torch_cuda_baseline(dev, args.pairs_per_gpu, args.steps, args.warmup)
+    print(json.dumps({"impl": "torch_cuda", "metric": METRIC, "value": r["value"], "unit": "px/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling or "strong",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_config(1, args.scaling or "strong", args.pairs_per_gpu),
+                      "torch_cuda_baseline": r, "gpu_launches": 0}))
+
+
+def pin_rank_to_cores(local, local_world):
+    """Give each rank its own slice of the host cores (the H2D copies of the end-to-end leg are issued from this process; all GPUs
+    of the box hang off one NUMA node, so the slice only keeps the ranks' copy / launch threads off each other's cores)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(1, local_world)
+        if per >= 1 and local_world > 1:
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+            torch.set_num_threads(max(1, per))
+            return per
+    except (AttributeError, OSError):
+        pass
+    return None
 
 
 def run_ours(args):
@@ -172,19 +268,23 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores_per_rank = pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if args.nccl_max_ctas > 0:          # the bucket's all-reduce shares the SMs with an issue-bound kernel: keep NCCL narrow
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))
         dist.init_process_group("nccl", device_id=dev)
-    P = args.pairs_per_gpu
+    scaling = args.scaling or "strong"
+    G_PAIRS = args.pairs_per_gpu                      # 256: the global batch in strong mode, the per-rank batch in weak mode
     clocks = ClockSampler(local) if rank == 0 else None
+    ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    # ---- synthetic inputs, resident in HBM (2.2 GB per GPU >> 126 MB L2) ------------------------------
-    chunks = [make_pairs(min(32, P - s), H, W, "icl", seed=1000 * rank + s, device=dev) for s in range(0, P, 32)]
-    d = {k: torch.cat([c[k] for c in chunks]) for k in chunks[0]}
-    del chunks
-    src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)   # NCHW views of NHWC memory
-    plan = ops.WarpPhotoPlan(P, H, W, dev, overlap_zero_fill=not args.no_overlap_zero_fill)
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     bucket = None
     if world > 1:       # stands in for the depth net's trainable parameters: one flat fp32 gradient bucket of its size
         from e2e_slam_b200.distributed import FlatGradBucket
@@ -192,58 +292,102 @@ def run_ours(args):
         stand_in.grad = torch.full_like(stand_in, float(rank))
         bucket = FlatGradBucket([stand_in], device=dev)
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    kargs = (d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+    def make_shard(mode):
+        """This rank's pairs, resident in HBM.  strong: rank r owns pairs r::G of the global 256; weak: 256 pairs of its own."""
+        P = G_PAIRS if (mode == "weak" or world == 1) else len(range(rank, G_PAIRS, world))
+        chunks = [make_pairs(min(32, P - s), H, W, "icl", seed=1000 * rank + s, device=dev) for s in range(0, P, 32)]
+        d = {k: torch.cat([c[k] for c in chunks]) for k in chunks[0]}
+        return P, d
 
-    def step(record):
-        """One pass of the hot path over this rank's pairs: loss + gradients to depth, source image and pose in
-        ONE sweep (WarpPhotoPlan.value_and_grad -> e2e_warp_photo_vg: streaming kernel + two fixed-order reductions).  grad_src is
-        accumulated with atomics, so it is zero-filled every step: of two buffers, the one for the NEXT step is cleared on a
-        side stream while this step's kernel runs."""
-        if world > 1:   # depth-net gradient bucket all-reduce on the side stream, overlapped with this step's kernels
-            bucket.start()
-        e0, e1 = ev(), ev()
-        e0.record()
-        loss, _, _, _ = plan.value_and_grad(*kargs)
-        e1.record()
+    def device_leg(mode, steps, warmup, with_clocks):
+        """K timed steps of the hot path on data resident in HBM; returns a dict (times are the max over ranks)."""
+        P, d = make_shard(mode)
+        src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)   # NCHW views of NHWC memory
+        plan = ops.WarpPhotoPlan(P, H, W, dev, overlap_zero_fill=not args.no_overlap_zero_fill)
+        kargs = (d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+
+        def step(record):
+            """One pass of the hot path over this rank's pairs: loss + gradients to depth, source image and pose in ONE sweep
+            (WarpPhotoPlan.value_and_grad -> e2e_warp_photo_vg: streaming kernel + two fixed-order reductions).  grad_src is
+            accumulated with atomics, so it is zero-filled every step: of two buffers, the one for the NEXT step is cleared on a
+            side stream while this step's kernel runs."""
+            if world > 1:   # depth-net gradient bucket all-reduce on the side stream, overlapped with this step's kernels
+                bucket.start()
+            e0, e1 = ev(), ev()
+            e0.record()
+            loss, _, _, _ = plan.value_and_grad(*kargs)
+            e1.record()
+            if world > 1:
+                bucket.finish()
+            if record is not None:
+                record.append((e0, e1))
+            return loss
+
+        for _ in range(warmup):
+            step(None)
+        sync_all()
+        l0 = ops.launch_count()
+        recs = []
+        t_start, t_end = ev(), ev()
+        wall0 = time.time()
+        t_start.record()
+        for _ in range(steps):
+            loss = step(recs)
+        t_end.record()
+        sync_all()
+        wall1 = time.time()
+        launches = ops.launch_count() - l0
+        ms = t_start.elapsed_time(t_end)
+        vg_ms = [a.elapsed_time(b) for a, b in recs]
+        kern_ms = sum(vg_ms) / len(vg_ms)
         if world > 1:
-            bucket.finish()
-        if record is not None:
-            record.append((e0, e1))
-        return loss
+            t = torch.tensor([ms, kern_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, kern_ms = float(t[0]), float(t[1])
+        glob = P * world if (mode == "weak" or world == 1) else G_PAIRS
+        return {"mode": mode, "pairs_per_rank": P, "global_pairs": glob, "elapsed_ms": ms, "ms_per_step": ms / steps,
+                "value": glob * H * W * steps / (ms * 1e-3), "kernel_ms_per_step": kern_ms, "launches": launches, "loss": float(loss),
+                "wall": (wall0, wall1), "plan": plan, "data": d, "kargs": kargs}
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    main = device_leg(scaling, args.steps, args.warmup, True)
+    clk = clocks.stop(*main["wall"]) if clocks else None
+    main_elapsed_ms, main_launches, main_loss, main_kernel_ms = main["elapsed_ms"], main["launches"], main["loss"], main["kernel_ms_per_step"]
+    P, d, plan, kargs = main["pairs_per_rank"], main["data"], main["plan"], main["kargs"]
+    src, tgt = kargs[4], kargs[5]
+    px_per_step = main["global_pairs"] * H * W
+    other = None
+    if world > 1 and not args.one_mode:                   # the other scaling mode, reported next to the headline
+        om = "weak" if scaling == "strong" else "strong"
+        if om == "weak":
+            del main["plan"], main["data"], main["kargs"], plan, d, kargs, src, tgt
+            torch.cuda.empty_cache()
+        o = device_leg(om, args.steps, args.warmup, False)
+        other = {k: o[k] for k in ("mode", "pairs_per_rank", "global_pairs", "ms_per_step", "value", "kernel_ms_per_step")}
+        other["unit"] = "px/s"
+        if om == "weak":                                  # continue the secondary legs on the strong shard
+            del o
+            torch.cuda.empty_cache()
+            P, d = make_shard(scaling)
+            src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)
+            plan = ops.WarpPhotoPlan(P, H, W, dev, overlap_zero_fill=not args.no_overlap_zero_fill)
+            kargs = (d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+        else:
+            del o
 
-    for _ in range(args.warmup):
-        step(None)
-    sync_all()
-    launches0 = ops.launch_count()
-    recs = []
-    t_start, t_end = ev(), ev()
-    wall0 = time.time()
-    t_start.record()
-    for _ in range(args.steps):
-        loss = step(recs)
-    t_end.record()
-    sync_all()
-    wall1 = time.time()
-    launches = ops.launch_count() - launches0
-    elapsed_ms = t_start.elapsed_time(t_end)
-    vg_ms = [e0.elapsed_time(e1) for e0, e1 in recs]
-    clk = clocks.stop(wall0, wall1) if clocks else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t)
-    px_per_step = P * H * W * world
-    value = px_per_step * args.steps / (elapsed_ms * 1e-3)
+    def rewarm(ms=60.0):
+        """Keep the GPU busy for ~ms before a secondary leg (the clocks drop while the host prepares the next workload)."""
+        a, b = ev(), ev()
+        a.record()
+        while True:
+            plan.value_and_grad(*kargs)
+            b.record()
+            b.synchronize()
+            if a.elapsed_time(b) >= ms:
+                return
 
-    # ---- secondary: the separate forward / backward kernels (loss-map path), outside the timed region ----
-    def timed(fn, n=3):
-        fn()
+    def timed(fn, n=3, warm=1):
+        for _ in range(warm):
+            fn()
         a, b = ev(), ev()
         a.record()
         for _ in range(n):
@@ -251,6 +395,23 @@ def run_ours(args):
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
+
+    def timed_median(fn, n=20, warm=3):
+        """Median of n individually event-timed calls after `warm` warm-ups (secondary, latency-type numbers)."""
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = ev(), ev()
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts), min(ts), max(ts)
+
+    # ---- secondary: the separate forward / backward kernels (loss-map path), outside the timed region ----
     fwd_avg = timed(lambda: plan.forward(*kargs))
     bwd_avg = timed(lambda: plan.backward(*kargs))
 
@@ -353,6 +514,8 @@ def run_ours(args):
         e2e_u8 = {"value": px_per_step * e2e_steps / dt8, "unit": "px/s", "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": 4,
                   "loss": l8, "note": "frames uploaded as uint8 and divided by 255 on the device (bit-identical to the host division); "
                                       "depth, K, T as fp32"}
+        del host_u8
+    del host
 
     if rank != 0:
         if world > 1:
@@ -361,17 +524,21 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peak, peak_src = measured_peak()
-    vg_avg = sum(vg_ms) / len(vg_ms)
+    vg_avg = main_kernel_ms
     npx = P * H * W
     ach = ALG_BYTES_STEP * npx / (vg_avg * 1e-3) / 1e9
     traffic = ncu_traffic() or {}
-    roof = {"bound": "hbm", "kernel": "warp_photo_stream_kernel (+ loss / grad_P reductions)", "achieved": ach, "peak": peak,
+    zero_fill_bytes = 12 * npx
+    roof = {"bound": "hbm", "kernel": "warp_photo_stream_ws_kernel (+ loss / grad_P reductions)", "achieved": ach, "peak": peak,
             "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get("vg_bytes_per_launch"), "peak_source": peak_src,
-            "algorithmic_bytes_per_px": ALG_BYTES_STEP, "ms_per_launch": vg_avg,
+            "algorithmic_bytes_per_px": ALG_BYTES_STEP, "ms_per_launch": vg_avg, "pairs_per_launch": P,
             "note": "72 B/px = SURVEY 8(d) fwd+bwd figure (36+36*S); the single sweep itself moves 44 B/px "
                     "(read depth 4 + target 12 + source 12, write grad_depth 4 + grad_src 12)",
             "achieved_single_sweep_44B": ALG_BYTES_SWEEP * npx / (vg_avg * 1e-3) / 1e9,
-            "limiter": "fp32 issue slots (bit-exact 3x3 window sums: ~1100 instructions per pixel), see DESIGN.md section 5"}
+            "zero_fill_bytes_per_step": zero_fill_bytes,
+            "zero_fill_note": "grad_src is accumulated with red.global.add, so it is cleared every step (12 B/px written by a memset on a side "
+                              "stream, overlapped with the kernel); not part of `traffic`, which is the kernel's own DRAM bytes",
+            "limiter": "fp32 issue slots (bit-exact 3x3 window sums), see DESIGN.md section 5"}
     roof_two = {"fwd_kernel_ms": fwd_avg, "bwd_kernel_ms_incl_zero_fill": bwd_avg,
                 "fwd_frac": ALG_BYTES_FWD * npx / (fwd_avg * 1e-3) / 1e9 / peak,
                 "bwd_frac": ALG_BYTES_BWD * npx / (bwd_avg * 1e-3) / 1e9 / peak,
@@ -381,35 +548,27 @@ def run_ours(args):
                         "gradient (streaming kernel); map_path = what patch.fuse() gives the unmodified scripts: forward keeping loss map / "
                         "synthesized frame / valid mask + .mean(1).mean() + backward through autograd (one sweep + rescale)"}
 
-    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------------------------
-    cpu = None
-    if world == 1 and not args.skip_cpu:
-        threads = os.cpu_count() or 1
-        best, mean, times = cpu_reference_px_per_s(args.cpu_pairs, reps=3, warm=1, threads=threads)
-        cpu = {"value": best, "unit": "px/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_pairs} of the 256 pairs, 480x640, fwd+bwd, torch-op restatement of the reference "
-                         f"(oracle/torch_oracle.py), best of 3 after 1 warm-up, {threads} threads"}
-
     # ---- secondary: one key-frame pair (config C1 shape) -- launch-latency bound, reported as latency ------------
     single = None
     if world == 1:
         p1 = ops.WarpPhotoPlan(1, H, W, dev)
         a1 = tuple(t[:1] for t in (d["depth"], d["inv_K"], d["K"], d["T"])) + (src[:1], tgt[:1])
+        rewarm()
         l0 = ops.launch_count()
-        eager_ms = timed(lambda: p1.value_and_grad(*a1), n=50)
-        per_call = (ops.launch_count() - l0) // 51
+        eager_ms, _, _ = timed_median(lambda: p1.value_and_grad(*a1), n=50, warm=5)
+        per_call = (ops.launch_count() - l0) // 55
         graph_ms = None
         try:                                            # the same call captured once and replayed as a CUDA graph
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 p1.value_and_grad(*a1)
-            graph_ms = timed(g.replay, n=200)
+            graph_ms, _, _ = timed_median(g.replay, n=100, warm=5)
         except Exception as e:                          # capture is an optimisation, not part of the contract
             graph_ms = None
             sys.stderr.write(f"single-pair graph capture failed: {e}\n")
         single = {"workload": "C1 single ICL-shaped 480x640 pair, loss + gradients to depth / source / pose", "eager_us": eager_ms * 1e3,
                   "cuda_graph_us": None if graph_ms is None else graph_ms * 1e3, "launches_per_call": per_call,
-                  "px_per_s_graph": None if graph_ms is None else H * W / (graph_ms * 1e-3)}
+                  "px_per_s_graph": None if graph_ms is None else H * W / (graph_ms * 1e-3), "timing": "median of 50 / 100 event-timed calls"}
 
     # ---- secondary: point supervision (config C2 / online loop): one live frame against a 2 M-point map ----------
     knn = None
@@ -426,9 +585,11 @@ def run_ours(args):
         def knn_step():
             q_ = qry.detach().requires_grad_(True)
             losses.point_supervision_loss(q_, Tq, ref).backward()
-        knn_ms = timed(knn_step, n=5)
+        rewarm()
+        knn_ms, knn_min, knn_max = timed_median(knn_step, n=20, warm=3)
         knn = {"workload": "compute_3d_loss (online_adaption.py:638-645): 307 200 live points, fused 4x4 transform, nearest of a 2 000 000-point map, "
-                           "loss + gradient", "ms": knn_ms, "queries_per_s": P1n / (knn_ms * 1e-3),
+                           "loss + gradient", "ms": knn_ms, "ms_min": knn_min, "ms_max": knn_max, "timing": "median of 20 event-timed calls after 3 warm-ups",
+               "queries_per_s": P1n / (knn_ms * 1e-3),
                "brute_force_pairs_avoided": float(P1n) * P2n, "kernel": "uniform-grid exact kNN (bit-identical to brute force)"}
         del ref, qry, uv
 
@@ -437,6 +598,7 @@ def run_ours(args):
     if world == 1 and not args.skip_fusion:
         try:
             from e2e_slam_b200 import c2_bench
+            rewarm()
             c2 = c2_bench.run(dev)
         except ImportError:
             c2 = None
@@ -446,27 +608,54 @@ def run_ours(args):
     if world == 1 and not args.skip_fusion:
         try:
             from e2e_slam_b200 import fusion_bench
+            rewarm()
             fusion = fusion_bench.run(dev)
         except ImportError:
             fusion = None
 
+    # ---- the unfused torch-CUDA baseline on the same GPU (rank 0, N = 1) ---------------------------------
+    tc = None
+    if world == 1 and not args.skip_torch_cuda:
+        del plan, kargs, src, tgt, d, main
+        torch.cuda.empty_cache()
+        try:
+            tc = torch_cuda_baseline(dev, G_PAIRS, steps=3, warmup=1)
+        except Exception as e:                            # a baseline, never a reason to lose the line
+            tc = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
+
+    # ---- CPU baseline: the whole workload once, LAST (the GPU idles meanwhile) --------------------------
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        cpu_reference_step(CPU_CHUNK, threads)
+        dt = cpu_reference_step(args.cpu_pairs, threads)
+        cpu = {"value": args.cpu_pairs * H * W / dt, "unit": "px/s", "cores": threads, "kind": "port", "seconds": dt,
+               "sample": f"all {args.cpu_pairs} pairs of the workload once (chunks of {CPU_CHUNK}) after a one-chunk warm-up, 480x640, fwd+bwd, "
+                         f"torch-op restatement of the reference (oracle/torch_oracle.py), {threads} threads"}
+
+    cfg = base_config(world, scaling, G_PAIRS)
+    cfg["global_pairs"] = P * world if scaling == "weak" else G_PAIRS
+    cfg.update({"pairs_per_gpu": P, "parallelism": f"dp{world}",
+                "l2_policy": "inputs (2.2 GB per 256 pairs) larger than L2; no explicit flush" if P * 8.6e6 > 200e6 else
+                             "inputs of one step exceed L2 (126 MB); no explicit flush",
+                "zero_fill": "grad_src is cleared every step; the buffer for the next step is cleared on a side stream during this step's kernel",
+                "collective": None if world == 1 else f"NCCL all-reduce of {GRAD_BUCKET_ELEMS} fp32 depth-net gradients per step, overlapped"
+                                                       + (f", NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}" if os.environ.get("NCCL_MAX_CTAS") else ""),
+                "cores_per_rank": cores_per_rank})
     out = {
-        "metric": METRIC, "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4 batched-256: 256 ICL-shaped 480x640 key-frame pairs per GPU, S=1, fused warp+SSIM/L1 loss + gradients "
-                               "(to depth, source image, pose) in one sweep", "pairs_per_gpu": P, "global_pairs": P * world,
-                   "height": H, "width": W, "source_frames": 1, "padding_mode": "border", "photometric_mask": True,
-                   "l2_policy": "inputs (2.2 GB/GPU) larger than L2; no explicit flush",
-                   "zero_fill": "grad_src (0.94 GB) is cleared every step; the buffer for the next step is cleared on a side stream during this step's kernel",
-                   "collective": None if world == 1 else f"NCCL all-reduce of {GRAD_BUCKET_ELEMS} fp32 depth-net gradients per step, overlapped"},
+        "metric": METRIC, "value": px_per_step * args.steps / (main_elapsed_ms * 1e-3), "unit": "px/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main_elapsed_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                 "steps": e2e_steps, "loss": lval, "h2d_chunks": n_chunks},
         "e2e_u8_frames": e2e_u8,
-        "gpu_launches": launches,
+        "gpu_launches": main_launches,
         "roofline": roof, "two_kernel_path": roof_two,
-        "cpu_baseline": cpu, "fusion": fusion, "single_pair": single, "c2_refinement_step": c2, "point_supervision": knn, "loss": float(loss),
+        ("weak_scaling" if scaling == "strong" else "strong_scaling"): other,
+        "cpu_baseline": cpu, "torch_cuda_baseline": tc, "fusion": fusion, "single_pair": single, "c2_refinement_step": c2,
+        "point_supervision": knn, "loss": main_loss,
     }
     print(json.dumps(out))
     if world > 1:
@@ -478,16 +667,23 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=256)
-    ap.add_argument("--cpu-pairs", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_cuda"])
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="N > 1: strong = 256 pairs sharded over the ranks (BASELINE C4, default), weak = 256 pairs per rank")
+    ap.add_argument("--one-mode", action="store_true", help="N > 1: skip the other scaling mode's secondary leg")
+    ap.add_argument("--pairs-per-gpu", type=int, default=256, help="256: the global batch (strong) / the per-rank batch (weak)")
+    ap.add_argument("--cpu-pairs", type=int, default=256)
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--nccl-max-ctas", type=int, default=0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-fusion", action="store_true")
+    ap.add_argument("--skip-torch-cuda", action="store_true")
     ap.add_argument("--no-overlap-zero-fill", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_cuda":
+        run_torch_cuda(args)
     else:
         run_ours(args)
 

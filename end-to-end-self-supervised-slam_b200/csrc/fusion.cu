@@ -276,6 +276,65 @@ __global__ void __launch_bounds__(FU_NT) associate_pass2_kernel(const AssocParam
 }
 
 // ---------------------------------------------------------------------------------------------
+// e2e_fusion_active_points: gradslam.slam.fusionutils.find_active_map_points (imported at online_adaption.py:35; SURVEY 8(a) a18,
+// appendix B step 1) as a stand-alone entry: rows (b, n, h, w) int64 of the map points that lie in front of the live camera and
+// project into the frame, ORDERED BY n (stream compaction: count per chunk | scan | write).  Same arithmetic as the association
+// kernels (assoc_pixel), so the rows are exactly the candidates those kernels consider.
+// ---------------------------------------------------------------------------------------------
+struct ActiveParams {
+    const float *pts;
+    long long n;
+    const float *K, *pose;
+    int H, W;
+    float u_hi, v_hi;
+    long long batch;
+    int *pix;              // [n] pixel of every map point (-1 = inactive)
+    int *chunk_counts;     // [nchunks], then exclusive offsets in place
+    long long *rows;       // [n_active, 4]
+};
+
+__global__ void __launch_bounds__(FU_NT) active_count_kernel(const ActiveParams p)
+{
+    __shared__ Cam c;
+    __shared__ int wsum[FU_NT / 32];
+    stage_cam(p.K, p.pose, &c);
+    const AssocConst a{p.H, p.W, 0.f, 0.f, p.u_hi, p.v_hi};
+    const long long n = (long long)blockIdx.x * FU_NT + threadIdx.x;
+    int pix = -1;
+    if (n < p.n) {
+        pix = assoc_pixel(c, a, p.pts[n * 3], p.pts[n * 3 + 1], p.pts[n * 3 + 2]);
+        p.pix[n] = pix;
+    }
+    const int cnt = __popc(__ballot_sync(0xffffffffu, pix >= 0));
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < FU_NT / 32; w++) t += wsum[w];
+        p.chunk_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(FU_NT) active_write_kernel(const ActiveParams p)
+{
+    __shared__ int woff[FU_NT / 32];
+    const long long n = (long long)blockIdx.x * FU_NT + threadIdx.x;
+    const int pix = (n < p.n) ? p.pix[n] : -1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned ballot = __ballot_sync(0xffffffffu, pix >= 0);
+    if (lane == 0) woff[wid] = __popc(ballot);
+    __syncthreads();
+    if (pix < 0) return;
+    long long slot = p.chunk_counts[blockIdx.x] + __popc(ballot & ((1u << lane) - 1));
+    for (int w = 0; w < wid; w++) slot += woff[w];
+    long long *r = p.rows + slot * 4;
+    r[0] = p.batch;
+    r[1] = n;
+    r[2] = pix / p.W;
+    r[3] = pix - (pix / p.W) * p.W;
+}
+
+// ---------------------------------------------------------------------------------------------
 // e2e_fusion_merge_append: merge + count | scan of chunk counts | append
 // ---------------------------------------------------------------------------------------------
 struct FuseParams {
@@ -380,7 +439,7 @@ __global__ void __launch_bounds__(1024) fuse_scan_kernel(int *chunk_counts, int 
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) n_out[0] = n_map[0] + (long long)carry;
+    if (threadIdx.x == 0) n_out[0] = (n_map ? n_map[0] : 0ll) + (long long)carry;
 }
 
 __global__ void __launch_bounds__(FU_NT) fuse_append_kernel(const FuseParams p)
@@ -946,6 +1005,39 @@ int e2e_fusion_associate(const float *map_points, const float *map_normals, cons
     associate_pass2_kernel<<<grid, FU_NT, 0, st>>>(p);
     count_launch(2);
     return finish_launch("fusion_associate");
+}
+
+size_t e2e_fusion_active_points_workspace_bytes(long long n)
+{
+    const size_t nchunks = (size_t)((n + FU_NT - 1) / FU_NT);
+    return (size_t)(n > 0 ? n : 0) * sizeof(int) + nchunks * sizeof(int) + 256;
+}
+
+int e2e_fusion_active_points(const float *map_points, long long n, const float *K, const float *pose, int H, int W,
+                             long long batch_index, long long *rows, long long *n_active,
+                             void *workspace, size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    E2E_REQUIRE(K && pose && n_active && H > 0 && W > 0 && n >= 0, "fusion_active_points: bad arguments");
+    E2E_REQUIRE((long long)H * W < (1ll << 31), "fusion_active_points: image too large");
+    if (n == 0) {
+        cudaMemsetAsync(n_active, 0, sizeof(long long), st);
+        return finish_launch("fusion_active_points");
+    }
+    E2E_REQUIRE(map_points && rows, "fusion_active_points: null map / rows");
+    const long long nchunks = (n + FU_NT - 1) / FU_NT;
+    E2E_REQUIRE(nchunks < (1ll << 31), "fusion_active_points: map too large");
+    E2E_REQUIRE(workspace && workspace_bytes >= (size_t)n * sizeof(int) + (size_t)nchunks * sizeof(int), "fusion_active_points: workspace too small");
+    ActiveParams p;
+    p.pts = map_points; p.n = n; p.K = K; p.pose = pose; p.H = H; p.W = W;
+    p.u_hi = (float)((double)W - 0.999); p.v_hi = (float)((double)H - 0.999);
+    p.batch = batch_index;
+    p.pix = (int *)workspace; p.chunk_counts = p.pix + n; p.rows = rows;
+    active_count_kernel<<<(unsigned)nchunks, FU_NT, 0, st>>>(p);
+    fuse_scan_kernel<<<1, 1024, 0, st>>>(p.chunk_counts, (int)nchunks, nullptr, n_active);
+    active_write_kernel<<<(unsigned)nchunks, FU_NT, 0, st>>>(p);
+    count_launch(3);
+    return finish_launch("fusion_active_points");
 }
 
 size_t e2e_fusion_workspace_bytes(int H, int W)

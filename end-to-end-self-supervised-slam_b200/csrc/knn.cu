@@ -94,6 +94,62 @@ __global__ void __launch_bounds__(KNN_NT) knn1_bwd_kernel(const float *query, co
     }
 }
 
+
+// gradslam.geometry.geometryutils.transform_pointcloud (online_adaption.py:642): R p + t for (N,3) points, accumulated left to
+// right like the oracle (and like load_query above, so that transform-then-kNN equals the fused query load bit for bit).
+__global__ void __launch_bounds__(KNN_NT) transform_points_fwd_kernel(const float *pts, const float *T, long long n, float *out)
+{
+    for (long long i = (long long)blockIdx.x * KNN_NT + threadIdx.x; i < n; i += (long long)gridDim.x * KNN_NT) {
+        float q[3];
+        load_query(pts, T, i, q);
+        out[i * 3] = q[0]; out[i * 3 + 1] = q[1]; out[i * 3 + 2] = q[2];
+    }
+}
+
+__global__ void __launch_bounds__(KNN_NT) transform_points_bwd_kernel(const float *T, const float *g, long long n, float *gp)
+{
+    for (long long i = (long long)blockIdx.x * KNN_NT + threadIdx.x; i < n; i += (long long)gridDim.x * KNN_NT) {
+        const float d0 = g[i * 3], d1 = g[i * 3 + 1], d2 = g[i * 3 + 2];
+        gp[i * 3] = T[0] * d0 + T[4] * d1 + T[8] * d2;              // R^T g
+        gp[i * 3 + 1] = T[1] * d0 + T[5] * d1 + T[9] * d2;
+        gp[i * 3 + 2] = T[2] * d0 + T[6] * d1 + T[10] * d2;
+    }
+}
+
+// color_points_loss (loss/losses.py:65-82): mean | noisy_col[i] - gt_col[idx[i]] | over the 3 P1 colour values; per-CTA partial
+// sums, reduced in fixed order by the caller's second launch (deterministic).
+__global__ void __launch_bounds__(KNN_NT) color_points_fwd_kernel(const float *gt, const float *noisy, const long long *idx, long long P1,
+                                                                  float *partial)
+{
+    __shared__ float scratch[KNN_NT / 32];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * KNN_NT + threadIdx.x; i < P1; i += (long long)gridDim.x * KNN_NT) {
+        const long long j = idx[i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) acc += fabsf(noisy[i * 3 + c] - gt[j * 3 + c]);
+    }
+    const float t = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(KNN_NT) color_points_bwd_kernel(const float *gt, const float *noisy, const long long *idx, long long P1,
+                                                                  const float *g, float scale, float *g_noisy, float *g_gt)
+{
+    const float gs = scale * (g ? __ldg(g) : 1.0f);
+    for (long long i = (long long)blockIdx.x * KNN_NT + threadIdx.x; i < P1; i += (long long)gridDim.x * KNN_NT) {
+        const long long j = idx[i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float d = noisy[i * 3 + c] - gt[j * 3 + c];
+            const float s = (d > 0.f) ? gs : ((d < 0.f) ? -gs : 0.f);       // torch: sign(0) = 0
+            if (g_noisy) g_noisy[i * 3 + c] = s;
+            if (g_gt && s != 0.f) atomicAdd(g_gt + j * 3 + c, -s);
+        }
+    }
+}
+
+int launch_reduce_partials(const float *partial, long long n, double scale, float *out, cudaStream_t st);   // warp_photo.cu
+
 }  // namespace e2e
 
 using namespace e2e;
@@ -122,6 +178,55 @@ int e2e_knn1_bwd(const float *query, const float *transform, const float *ref, l
     knn1_bwd_kernel<<<(unsigned)blocks, KNN_NT, 0, (cudaStream_t)stream>>>(query, transform, ref, P1, idx, grad_dist2, grad_query, grad_ref);
     count_launch();
     return finish_launch("knn1_bwd");
+}
+
+static unsigned points_grid(long long n)
+{
+    long long blocks = (n + KNN_NT - 1) / KNN_NT;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+int e2e_transform_points_fwd(const float *points, const float *transform, long long n, float *out, void *stream)
+{
+    E2E_REQUIRE(transform && n >= 0 && (n == 0 || (points && out)), "transform_points: bad arguments");
+    if (n == 0) return 0;
+    transform_points_fwd_kernel<<<points_grid(n), KNN_NT, 0, (cudaStream_t)stream>>>(points, transform, n, out);
+    count_launch();
+    return finish_launch("transform_points_fwd");
+}
+
+int e2e_transform_points_bwd(const float *transform, const float *grad_out, long long n, float *grad_points, void *stream)
+{
+    E2E_REQUIRE(transform && n >= 0 && (n == 0 || (grad_out && grad_points)), "transform_points_bwd: bad arguments");
+    if (n == 0) return 0;
+    transform_points_bwd_kernel<<<points_grid(n), KNN_NT, 0, (cudaStream_t)stream>>>(transform, grad_out, n, grad_points);
+    count_launch();
+    return finish_launch("transform_points_bwd");
+}
+
+size_t e2e_color_points_workspace_bytes(long long P1) { return (size_t)points_grid(P1) * sizeof(float) + 256; }
+
+int e2e_color_points_fwd(const float *gt_colors, const float *noisy_colors, const long long *idx, long long P1, float *loss,
+                         void *workspace, size_t workspace_bytes, void *stream)
+{
+    E2E_REQUIRE(gt_colors && noisy_colors && idx && loss && P1 > 0, "color_points: bad arguments");
+    const unsigned grid = points_grid(P1);
+    E2E_REQUIRE(workspace && workspace_bytes >= grid * sizeof(float), "color_points: workspace too small");
+    color_points_fwd_kernel<<<grid, KNN_NT, 0, (cudaStream_t)stream>>>(gt_colors, noisy_colors, idx, P1, (float *)workspace);
+    count_launch();
+    if (int rc = finish_launch("color_points_fwd")) return rc;
+    return launch_reduce_partials((const float *)workspace, grid, 1.0 / (3.0 * (double)P1), loss, (cudaStream_t)stream);
+}
+
+int e2e_color_points_bwd(const float *gt_colors, const float *noisy_colors, const long long *idx, long long P1, const float *grad_loss,
+                         float *grad_noisy, float *grad_gt, void *stream)
+{
+    E2E_REQUIRE(gt_colors && noisy_colors && idx && P1 > 0 && (grad_noisy || grad_gt), "color_points_bwd: bad arguments");
+    color_points_bwd_kernel<<<points_grid(P1), KNN_NT, 0, (cudaStream_t)stream>>>(gt_colors, noisy_colors, idx, P1, grad_loss,
+                                                                                  (float)(1.0 / (3.0 * (double)P1)), grad_noisy, grad_gt);
+    count_launch();
+    return finish_launch("color_points_bwd");
 }
 
 }  // extern "C"

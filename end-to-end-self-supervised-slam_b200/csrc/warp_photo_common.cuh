@@ -368,4 +368,5 @@ size_t stream_workspace_bytes(int B, int H, int W);
 int launch_stream(WPParams &p, int B, int H, int W, float *loss_mean, float *grad_P, void *workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_ssim_stream_bwd(WPParams &p, int B, int H, int W, cudaStream_t st);
 
+
 }  // namespace e2e

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "e2e_rgbd_maps": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     "e2e_rgbd_maps_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     "e2e_fusion_associate": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P]),
+    "e2e_fusion_active_points_workspace_bytes": (_SZ, [_LL]),
+    "e2e_fusion_active_points": (_I, [_P, _LL, _P, _P, _I, _I, _LL, _P, _P, _P, _SZ, _P]),
     "e2e_fusion_workspace_bytes": (_SZ, [_I, _I]),
     "e2e_fusion_merge_append": (_I, [_P, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _SZ, _P]),
     "e2e_knn1_grid_workspace_bytes": (_SZ, [_LL]),
@@ -72,6 +74,11 @@ _SIGNATURES = {
     "e2e_fusion_merge_append_bwd": (_I, [_P] * 11 + [_I, _I] + [_P] * 7),
     "e2e_knn1_fwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P]),
     "e2e_knn1_bwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P]),
+    "e2e_transform_points_fwd": (_I, [_P, _P, _LL, _P, _P]),
+    "e2e_transform_points_bwd": (_I, [_P, _P, _LL, _P, _P]),
+    "e2e_color_points_workspace_bytes": (_SZ, [_LL]),
+    "e2e_color_points_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
+    "e2e_color_points_bwd": (_I, [_P, _P, _P, _LL, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -277,8 +277,17 @@ class _KNN1(torch.autograd.Function):
         q, r = query.contiguous(), ref.contiguous()
         t = None if transform is None else f32(transform, "transform").contiguous()
         P1, P2 = q.shape[0], r.shape[0]
+        if ctx.needs_input_grad[2]:
+            raise NotImplementedError("nearest-neighbour distances are not differentiated w.r.t. the fused transform "
+                                      "(the reference detaches the pose, online_adaption.py:640-642); use slam.transform_pointcloud")
+        if P2 == 0:
+            raise ValueError("knn_points: the reference cloud is empty")
         dist2 = torch.empty(P1, dtype=torch.float32, device=q.device)
         idx = torch.empty(P1, dtype=torch.int64, device=q.device)
+        if P1 == 0:                                       # e.g. an all-invalid live depth map: nothing to match
+            ctx.save_for_backward(q, r, idx) if t is None else ctx.save_for_backward(q, r, idx, t)
+            ctx.mark_non_differentiable(idx)
+            return dist2, idx
         with torch.cuda.device(q.device):
             if _use_grid(P1, P2):      # same answer bit for bit, cost ~ P1 + P2 instead of P1 * P2
                 ws = _grid_for(r)
@@ -298,8 +307,8 @@ class _KNN1(torch.autograd.Function):
         g = f32(g, "grad").contiguous()
         gq = torch.empty_like(q) if ctx.needs_input_grad[0] else None
         gr = torch.zeros_like(r) if ctx.needs_input_grad[1] else None
-        if gq is None and gr is None:
-            return None, None, None
+        if (gq is None and gr is None) or q.shape[0] == 0:
+            return gq, gr, None
         with torch.cuda.device(q.device):
             check(lib().e2e_knn1_bwd(ptr(q), ptr(t), ptr(r), q.shape[0], r.shape[0], ptr(idx), ptr(g), ptr(gq), ptr(gr), stream_ptr()),
                   "e2e_knn1_bwd")
@@ -332,12 +341,47 @@ def knn_points_loss(gt_pointcloud, noisy_pointcloud):
     return torch.mean(distances), indexes
 
 
+class _ColorPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gt_col, noisy_col, idx):
+        gt, noisy, idx = gt_col.contiguous(), noisy_col.contiguous(), idx.contiguous()
+        P1 = noisy.shape[0]
+        loss = torch.empty(1, dtype=torch.float32, device=noisy.device)
+        nws = lib().e2e_color_points_workspace_bytes(P1)
+        ws = torch.empty(nws, dtype=torch.uint8, device=noisy.device)
+        with torch.cuda.device(noisy.device):
+            check(lib().e2e_color_points_fwd(ptr(gt), ptr(noisy), ptr(idx), P1, ptr(loss), ptr(ws), nws, stream_ptr()), "e2e_color_points_fwd")
+        ctx.save_for_backward(gt, noisy, idx)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        gt, noisy, idx = ctx.saved_tensors
+        g = f32(g, "grad").reshape(1).contiguous()
+        g_noisy = torch.empty_like(noisy) if ctx.needs_input_grad[1] else None
+        g_gt = torch.zeros_like(gt) if ctx.needs_input_grad[0] else None
+        if g_noisy is None and g_gt is None:
+            return None, None, None
+        with torch.cuda.device(noisy.device):
+            check(lib().e2e_color_points_bwd(ptr(gt), ptr(noisy), ptr(idx), noisy.shape[0], ptr(g), ptr(g_noisy), ptr(g_gt), stream_ptr()),
+                  "e2e_color_points_bwd")
+        return g_gt, g_noisy, None
+
+
 def color_points_loss(gt_pointcloud_color, noisy_pointcloud_color, indexes):
     """L1 between each noisy point's colour and the colour of its matched ground-truth point
-    (loss/losses.py:65-82); a gather + mean on the GPU."""
+    (loss/losses.py:65-82): gather + |.| + mean in one kernel (e2e_color_points_fwd), one kernel back."""
     if gt_pointcloud_color.shape[2] != noisy_pointcloud_color.shape[2]:
         raise ValueError("Number of axes is not the same in both pointclouds")
-    return torch.mean(torch.abs(noisy_pointcloud_color[0] - gt_pointcloud_color[0, indexes[0].long()]))
+    f32(gt_pointcloud_color, "gt_pointcloud_color"), f32(noisy_pointcloud_color, "noisy_pointcloud_color")
+    if gt_pointcloud_color.shape[2] != 3:
+        return torch.mean(torch.abs(noisy_pointcloud_color[0] - gt_pointcloud_color[0, indexes[0].long()]))
+    idx = indexes[0].long()
+    if idx.shape[0] != noisy_pointcloud_color.shape[1]:
+        raise ValueError(f"indexes ({idx.shape[0]}) must have one entry per noisy point ({noisy_pointcloud_color.shape[1]})")
+    if idx.shape[0] == 0:
+        return torch.full((), float("nan"), dtype=torch.float32, device=noisy_pointcloud_color.device)      # mean of an empty tensor
+    return _ColorPoints.apply(gt_pointcloud_color[0], noisy_pointcloud_color[0], idx)
 
 
 def point_supervision_loss(target_points, transform, global_points):

@@ -62,7 +62,7 @@ def install(grid_sample=False, keep_real_gradslam_datasets=True):
         raise ImportError("gradslam.datasets (ICL/TUM loaders) is dataset IO outside the hot path; install gradslam "
                           "to use it, or feed tensors of the same layout (see e2e_slam_b200.synthetic)")
 
-    fusionutils = _module("gradslam.slam.fusionutils", find_active_map_points=_find_active_map_points)
+    fusionutils = _module("gradslam.slam.fusionutils", find_active_map_points=slam.find_active_map_points)
     gs_slam = _module("gradslam.slam", PointFusion=slam.PointFusion, ICPSLAM=slam.ICPSLAM, fusionutils=fusionutils)
     geomutils = _module("gradslam.geometry.geometryutils", transform_pointcloud=slam.transform_pointcloud)
     se3utils = _module("gradslam.geometry.se3utils", se3_exp=odometry.se3_exp)
@@ -86,11 +86,6 @@ def install(grid_sample=False, keep_real_gradslam_datasets=True):
     sm.update({"chamferdist": cd, "chamferdist.chamfer": chamfer})
     if grid_sample:
         _patch_grid_sample()
-
-
-def _find_active_map_points(pointclouds, rgbdimages):
-    raise NotImplementedError("find_active_map_points is imported by online_adaption.py:35 but never called; the active-point "
-                              "test runs inside PointFusion.step's association kernel (e2e_fusion_associate)")
 
 
 _torch_grid_sample = torch.nn.functional.grid_sample

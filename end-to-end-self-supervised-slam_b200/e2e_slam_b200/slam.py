@@ -73,7 +73,16 @@ class RGBDImages:
             index = (index,)
         if len(index) > 2:
             raise IndexError("RGBDImages supports indexing of the batch and sequence dimensions only")
-        keep = tuple(slice(i, i + 1) if isinstance(i, int) else i for i in index)      # ints keep their dimension
+        dims = self._rgb.shape[:2]
+
+        def _keep(i, size):                                   # ints keep their dimension; negative ints count from the end
+            if not isinstance(i, int):
+                return i
+            j = i + size if i < 0 else i
+            if not (0 <= j < size):
+                raise IndexError(f"index {i} is out of bounds for dimension with size {size}")
+            return slice(j, j + 1)
+        keep = tuple(_keep(i, dims[d]) for d, i in enumerate(index))
         bidx = keep[0]
         return RGBDImages(self._rgb[keep], self._depth[keep], self._K[bidx],
                           None if self._poses is None else self._poses[keep])
@@ -445,15 +454,81 @@ class ICPSLAM(PointFusion):
         raise NotImplementedError("ICPSLAM is out of scope; use PointFusion (configs/config.yaml:29)")
 
 
+class _TransformPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, transform):
+        pts, T = points.contiguous(), transform.contiguous()
+        out = torch.empty_like(pts)
+        with torch.cuda.device(pts.device):
+            check(lib().e2e_transform_points_fwd(ptr(pts), ptr(T), pts.shape[0], ptr(out), stream_ptr()), "e2e_transform_points_fwd")
+        ctx.save_for_backward(pts, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pts, T = ctx.saved_tensors
+        g = f32(g, "grad").contiguous()
+        gp = gT = None
+        if ctx.needs_input_grad[0]:
+            gp = torch.empty_like(pts)
+            with torch.cuda.device(pts.device):
+                check(lib().e2e_transform_points_bwd(ptr(T), ptr(g), pts.shape[0], ptr(gp), stream_ptr()), "e2e_transform_points_bwd")
+        if ctx.needs_input_grad[1]:                           # 3x4 sums; the reference never asks for them on this path
+            gT = torch.zeros_like(T)
+            gT[:3, :3] = g.t() @ pts
+            gT[:3, 3] = g.sum(0)
+        return gp, gT
+
+
 def transform_pointcloud(pointcloud, transform):
     """gradslam.geometry.geometryutils.transform_pointcloud: (N,3) points by a 4x4 rigid transform
-    (online_adaption.py:642).  A 3x3 rotate-and-add; `losses.point_supervision_loss` fuses it into the
-    nearest-neighbour kernel's query load instead."""
+    (online_adaption.py:642): one kernel each way (e2e_transform_points_*), the same left-to-right arithmetic as the query
+    load that `losses.point_supervision_loss` fuses into the nearest-neighbour kernel."""
     if not torch.is_tensor(pointcloud) or not torch.is_tensor(transform):
         raise TypeError("pointcloud and transform must be tensors")
     if pointcloud.dim() != 2 or pointcloud.shape[1] != 3 or transform.shape != (4, 4):
         raise ValueError(f"expected pointcloud (N,3) and transform (4,4), got {tuple(pointcloud.shape)} / {tuple(transform.shape)}")
-    return pointcloud @ transform[:3, :3].t() + transform[:3, 3]
+    f32(pointcloud, "pointcloud"), f32(transform, "transform")
+    return _TransformPoints.apply(pointcloud, transform)
+
+
+def find_active_map_points(pointclouds, rgbdimages):
+    """gradslam.slam.fusionutils.find_active_map_points (imported by the reference at online_adaption.py:35):
+    the map points that lie in front of the live camera and project into the frame, as `pc2im_bnhw` (N_active, 4) int64 rows
+    (batch index, point index, pixel row, pixel column), ordered by (b, n).  `rgbdimages` is one live frame (sequence length 1)
+    with its pose set.  One host synchronisation per batch element (the result's size)."""
+    if not isinstance(pointclouds, Pointclouds):
+        raise TypeError(f"Expected pointclouds to be of type Pointclouds. Got {type(pointclouds)}.")
+    if not isinstance(rgbdimages, RGBDImages):
+        raise TypeError(f"Expected rgbdimages to be of type RGBDImages. Got {type(rgbdimages)}.")
+    if rgbdimages.shape[1] != 1:
+        raise ValueError(f"Expected rgbdimages to have sequence length of 1. Got {rgbdimages.shape[1]}.")
+    if rgbdimages.poses is None:
+        raise ValueError("rgbdimages.poses must be set")
+    B, _, H, W = rgbdimages.shape
+    if len(pointclouds) != B:
+        raise ValueError(f"Expected equal batch sizes for pointclouds and rgbdimages. Got {len(pointclouds)} and {B}.")
+    dev = rgbdimages.device
+    rows = []
+    for b in range(B):
+        m = pointclouds._maps[b]
+        n = m.count()
+        if n == 0:
+            continue
+        K = f32(rgbdimages.intrinsics[b, 0], "intrinsics").contiguous()
+        pose = f32(rgbdimages.poses[b, 0], "poses").detach().contiguous()
+        pts = m.pts.detach()
+        out = torch.empty(n, 4, dtype=torch.int64, device=dev)
+        n_act = torch.empty(1, dtype=torch.int64, device=dev)
+        nws = lib().e2e_fusion_active_points_workspace_bytes(n)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().e2e_fusion_active_points(ptr(pts), n, ptr(K), ptr(pose), H, W, b, ptr(out), ptr(n_act), ptr(ws), nws, stream_ptr()),
+                  "e2e_fusion_active_points")
+        rows.append(out[:int(n_act.item())])
+    if not rows:
+        return torch.zeros(0, 4, dtype=torch.int64, device=dev)
+    return torch.cat(rows, 0)
 
 
 def image_recover_slam(noisy_rgbd, slam, device):

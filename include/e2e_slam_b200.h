@@ -247,6 +247,15 @@ int e2e_fusion_associate(const float *map_points, const float *map_normals, cons
                          int H, int W, float dist_th, float dot_th,
                          unsigned long long *keys, int *candidates, long long *index_map, void *stream);
 
+/* find_active_map_points (gradslam.slam.fusionutils, imported by the reference at online_adaption.py:35):
+ * rows (batch_index, n, h, w) int64 of the map points in front of the live camera that project into the frame
+ * (-1e-3 < u < W - 0.999, -1e-3 < v < H - 0.999; pixel = round-half-even, clamped), ordered by n.  `rows` holds up to n rows;
+ * `n_active` (device int64[1]) receives the row count.  Three launches, no host synchronisation. */
+size_t e2e_fusion_active_points_workspace_bytes(long long n);
+int e2e_fusion_active_points(const float *map_points, long long n, const float *K, const float *pose, int H, int W,
+                             long long batch_index, long long *rows, long long *n_active,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 size_t e2e_fusion_workspace_bytes(int H, int W);
 
 int e2e_fusion_merge_append(float *map_points, float *map_normals, float *map_colors, float *map_ccount,
@@ -291,6 +300,20 @@ int e2e_knn1_fwd(const float *query, const float *transform, const float *ref, l
                  float *dist2, long long *idx, void *stream);
 int e2e_knn1_bwd(const float *query, const float *transform, const float *ref, long long P1, long long P2,
                  const long long *idx, const float *grad_dist2, float *grad_query, float *grad_ref, void *stream);
+
+/* gradslam.geometry.geometryutils.transform_pointcloud (online_adaption.py:642): out = R p + t for (n,3) points and a 4x4 rigid
+ * transform (left-to-right accumulation, identical to the query load fused into e2e_knn1_*); backward: grad_points = R^T grad_out. */
+int e2e_transform_points_fwd(const float *points, const float *transform, long long n, float *out, void *stream);
+int e2e_transform_points_bwd(const float *transform, const float *grad_out, long long n, float *grad_points, void *stream);
+
+/* color_points_loss (loss/losses.py:65-82): loss = mean | noisy_colors[i] - gt_colors[idx[i]] | over P1 x 3 values (idx from
+ * e2e_knn1_*).  Backward: grad_noisy [P1,3] (written), grad_gt [P2,3] (ACCUMULATED with atomics into a zero-filled buffer);
+ * grad_loss = device-resident upstream scalar (NULL = 1). */
+size_t e2e_color_points_workspace_bytes(long long P1);
+int e2e_color_points_fwd(const float *gt_colors, const float *noisy_colors, const long long *idx, long long P1, float *loss,
+                         void *workspace, size_t workspace_bytes, void *stream);
+int e2e_color_points_bwd(const float *gt_colors, const float *noisy_colors, const long long *idx, long long P1, const float *grad_loss,
+                         float *grad_noisy, float *grad_gt, void *stream);
 
 /* The same answer (bit for bit: distances in the same operation order, lowest index among exact ties) through a uniform grid
  * over the reference cloud, built on the device by the call itself; cost grows with P1 + P2 instead of P1 * P2.  The host

@@ -77,16 +77,12 @@ def rgbd_maps(depth, rgb, K, pose, sigma):
     return dict(vertex=V, normal=N.astype(np.float32), vertex_g=Vg, normal_g=Ng, alpha=alpha, valid=valid)
 
 
-def find_correspondences(points, normals, ccount, K, pose, maps, dist_th, dot_th):
-    """Steps 1-3 of update_map_fusion.  Returns rows (M,4) int64 = (b=0, n, h, w), sorted by n -- one row
-    per matched live pixel -- and the same information as index_map (H,W) int64 (-1 = no match)."""
-    points, normals, ccount, K = _f(points), _f(normals), _f(ccount).reshape(-1), _f(K)
-    Vg, Ng = maps["vertex_g"], maps["normal_g"]
-    H, W = Vg.shape[:2]
-    index_map = np.full((H, W), -1, dtype=np.int64)
+def find_active_map_points(points, K, pose, H, W, b=0):
+    """gradslam.slam.fusionutils.find_active_map_points (imported by the reference at online_adaption.py:35; SURVEY.md appendix B
+    step 1): rows (b, n, h, w) int64 of the map points in front of the live camera that project into the frame, ordered by n."""
+    points, K = _f(points), _f(K)
     if points.shape[0] == 0:
-        return np.zeros((0, 4), np.int64), index_map
-    # -- 1. active map points (find_active_map_points) --------------------------------------------
+        return np.zeros((0, 4), np.int64)
     Rinv, tinv = inverse_pose(pose)
     pc = np.stack([((Rinv[i, 0] * points[:, 0] + Rinv[i, 1] * points[:, 1]) + Rinv[i, 2] * points[:, 2]) + tinv[i]
                    for i in range(3)], -1).astype(np.float32)
@@ -99,6 +95,21 @@ def find_correspondences(points, normals, ccount, K, pose, maps, dist_th, dot_th
     n_idx = np.nonzero(in_frame)[0]
     w = np.clip(np.rint(uu[n_idx]), 0, W - 1).astype(np.int64)  # rint = round half to even, like torch.round [FROZEN]
     h = np.clip(np.rint(vv[n_idx]), 0, H - 1).astype(np.int64)
+    return np.stack([np.full_like(n_idx, b), n_idx, h, w], -1).astype(np.int64)
+
+
+def find_correspondences(points, normals, ccount, K, pose, maps, dist_th, dot_th):
+    """Steps 1-3 of update_map_fusion.  Returns rows (M,4) int64 = (b=0, n, h, w), sorted by n -- one row
+    per matched live pixel -- and the same information as index_map (H,W) int64 (-1 = no match)."""
+    points, normals, ccount, K = _f(points), _f(normals), _f(ccount).reshape(-1), _f(K)
+    Vg, Ng = maps["vertex_g"], maps["normal_g"]
+    H, W = Vg.shape[:2]
+    index_map = np.full((H, W), -1, dtype=np.int64)
+    if points.shape[0] == 0:
+        return np.zeros((0, 4), np.int64), index_map
+    # -- 1. active map points (find_active_map_points) --------------------------------------------
+    active = find_active_map_points(points, K, pose, H, W)
+    n_idx, h, w = active[:, 1], active[:, 2], active[:, 3]
     # -- 2. similar points (find_similar_map_points) ----------------------------------------------
     d = Vg[h, w] - points[n_idx]
     dist2 = ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).astype(np.float32)
