@@ -7,8 +7,8 @@ A single pair is launch-latency bound: the figure of merit is time
 graph."""
 import torch
 
-from . import losses, ops, view_synthesis
-from .synthetic import make_pairs
+from e2e_slam_b200 import losses, ops, view_synthesis
+from e2e_slam_b200.synthetic import make_pairs
 
 
 def _inputs(dev, H, W, map_points):

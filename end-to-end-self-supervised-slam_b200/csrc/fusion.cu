@@ -886,7 +886,10 @@ __device__ __forceinline__ void seq_frame(const SeqParams &p, SeqShared &sh, int
     SEQ_STAMP(4 + 3 * s);
 }
 
-__global__ void __launch_bounds__(SEQ_NT, 2) fusion_sequence_kernel(const SeqParams p)
+// The whole sequence loop of one CTA group.  Only blockIdx.x / gridDim.x are used below (pixel ranges, look-back counts, the grid
+// barrier's slots): a batch of independent sequences is therefore a 2-D grid, blockIdx.y = sequence, every sequence with its own
+// parameter block (own barrier word, counts and working buffers).
+__device__ __forceinline__ void fusion_sequence_body(const SeqParams &p)
 {
     __shared__ SeqShared sh;
     Cam *cams = sh.cams;
@@ -936,6 +939,21 @@ __global__ void __launch_bounds__(SEQ_NT, 2) fusion_sequence_kernel(const SeqPar
         p.col[n * 3] = cl.x; p.col[n * 3 + 1] = cl.y; p.col[n * 3 + 2] = cl.z;
         p.cc[n] = a.w;
     }
+}
+
+__global__ void __launch_bounds__(SEQ_NT, 2) fusion_sequence_kernel(const SeqParams p) { fusion_sequence_body(p); }
+
+// B independent sequences in ONE cooperative launch: grid (CTAs per sequence, B).  A single sequence is bound by dependent round
+// trips and two grid barriers per frame (8 % of DRAM peak, 30 % issue slots); sequences that share the SMs fill each other's
+// bubbles.  Parameter blocks live in global memory (one per sequence).
+__global__ void __launch_bounds__(SEQ_NT, 2) fusion_sequence_batch_kernel(const SeqParams *pp)
+{
+    __shared__ SeqParams sp;
+    static_assert(sizeof(SeqParams) % 4 == 0 && sizeof(SeqParams) / 4 <= SEQ_NT, "parameter block is staged by one pass of the CTA");
+    if (threadIdx.x < sizeof(SeqParams) / 4) reinterpret_cast<unsigned *>(&sp)[threadIdx.x] = reinterpret_cast<const unsigned *>(pp + blockIdx.y)[threadIdx.x];
+    __syncthreads();
+    const SeqParams p = sp;                 // a private copy: the fields the loop uses live in registers, like kernel parameters
+    fusion_sequence_body(p);
 }
 
 static inline int grid_for(long long n)
@@ -1099,9 +1117,10 @@ static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 // Grid of the whole-sequence kernel: every CTA must be resident (cooperative launch).  0 = not available.
 static int sequence_grid()
 {
-    static int grid = -1;
-    if (grid >= 0) return grid;
+    static int grid_dev[64];                       // per device, 0 = not yet known
     int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && grid_dev[dev & 63] > 0) return grid_dev[dev & 63];
+    int &grid = grid_dev[dev & 63];
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fusion_sequence_kernel, SEQ_NT, 0) != cudaSuccess) {
@@ -1165,6 +1184,30 @@ static int fusion_sequence_loop(const float *depth, const float *rgb, const floa
     return 0;
 }
 
+static SeqParams make_seq_params(const float *depth, const float *rgb, const float *K, const float *poses, int L, int H, int W,
+                                 float sigma, float dist_th, float dot_th, float *map_points, float *map_normals, float *map_colors,
+                                 float *map_ccount, long long *n_map, long long capacity, void *workspace)
+{
+    const size_t hw = (size_t)H * W;
+    SeqParams p;
+    p.depth = depth; p.rgb = rgb; p.K = K; p.poses = poses; p.L = L; p.H = H; p.W = W;
+    p.two_sigma2 = 2.0f * sigma * sigma;
+    p.ac = AssocConst{H, W, dist_th, dot_th, (float)((double)W - 0.999), (float)((double)H - 0.999)};
+    p.pts = map_points; p.nrm = map_normals; p.col = map_colors; p.cc = map_ccount; p.n_map = n_map; p.capacity = capacity;
+    unsigned char *w = (unsigned char *)workspace;
+    p.pts4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
+    p.nrm4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
+    p.col4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
+    for (int b = 0; b < 2; b++) {
+        p.vg4[b] = (float4 *)w;                     w += align256(hw * 16);
+        p.ng4[b] = (float4 *)w;                     w += align256(hw * 16);
+        p.keys[b] = (Key128 *)w;                    w += align256(hw * 16);
+    }
+    p.counts = (unsigned long long *)w;             w += align256(8 * 4096);
+    p.barrier = (unsigned *)w;
+    return p;
+}
+
 int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, const float *poses, int L, int H, int W,
                         float sigma, float dist_th, float dot_th,
                         float *map_points, float *map_normals, float *map_colors, float *map_ccount,
@@ -1188,22 +1231,8 @@ int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, co
     if (!coop)
         return fusion_sequence_loop(depth, rgb, K, poses, L, H, W, sigma, dist_th, dot_th, map_points, map_normals, map_colors,
                                     map_ccount, n_map, n_upper, capacity, workspace, stream);
-    SeqParams p;
-    p.depth = depth; p.rgb = rgb; p.K = K; p.poses = poses; p.L = L; p.H = H; p.W = W;
-    p.two_sigma2 = 2.0f * sigma * sigma;
-    p.ac = AssocConst{H, W, dist_th, dot_th, (float)((double)W - 0.999), (float)((double)H - 0.999)};
-    p.pts = map_points; p.nrm = map_normals; p.col = map_colors; p.cc = map_ccount; p.n_map = n_map; p.capacity = capacity;
-    unsigned char *w = (unsigned char *)workspace;
-    p.pts4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
-    p.nrm4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
-    p.col4 = (float4 *)w;                           w += align256((size_t)capacity * 16);
-    for (int b = 0; b < 2; b++) {
-        p.vg4[b] = (float4 *)w;                     w += align256(hw * 16);
-        p.ng4[b] = (float4 *)w;                     w += align256(hw * 16);
-        p.keys[b] = (Key128 *)w;                    w += align256(hw * 16);
-    }
-    p.counts = (unsigned long long *)w;             w += align256(8 * 4096);
-    p.barrier = (unsigned *)w;
+    SeqParams p = make_seq_params(depth, rgb, K, poses, L, H, W, sigma, dist_th, dot_th, map_points, map_normals, map_colors, map_ccount,
+                                  n_map, capacity, workspace);
     cudaStream_t st = (cudaStream_t)stream;
     // frame tags of the counts start at 1, the barrier counts arrivals from 0
     if (cudaMemsetAsync(p.counts, 0, align256(8 * 4096) + 256, st) != cudaSuccess) return finish_launch("fusion_sequence: memset");
@@ -1221,6 +1250,75 @@ int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, co
     }
     count_launch();
     return finish_launch("fusion_sequence");
+}
+
+size_t e2e_fusion_sequence_batch_workspace_bytes(int B, int H, int W, long long capacity)
+{
+    return (size_t)(B > 0 ? B : 0) * (align256(e2e_fusion_sequence_workspace_bytes(H, W, capacity)) + align256(sizeof(SeqParams))) + 256;
+}
+
+int e2e_fusion_sequence_batch(const float *depth, const float *rgb, const float *K, const float *poses, int B, int L, int H, int W,
+                              float sigma, float dist_th, float dot_th,
+                              float *map_points, float *map_normals, float *map_colors, float *map_ccount,
+                              long long *n_map, long long capacity, void *workspace, size_t workspace_bytes, void *stream)
+{
+    E2E_REQUIRE(depth && rgb && K && poses && map_points && map_normals && map_colors && map_ccount && n_map && workspace,
+                "fusion_sequence_batch: null argument");
+    E2E_REQUIRE(B >= 1 && L >= 0 && H > 0 && W > 0, "fusion_sequence_batch: bad sizes");
+    E2E_REQUIRE(capacity >= (long long)L * H * W, "fusion_sequence_batch: capacity must be >= L*H*W");
+    E2E_REQUIRE(workspace_bytes >= e2e_fusion_sequence_batch_workspace_bytes(B, H, W, capacity), "fusion_sequence_batch: workspace too small");
+    E2E_REQUIRE(sigma != 0.0f, "sigma must be non-zero");
+    E2E_REQUIRE((long long)H * W < (1ll << 31), "fusion_sequence_batch: image too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t hw = (size_t)H * W;
+    const size_t per_ws = align256(e2e_fusion_sequence_workspace_bytes(H, W, capacity));
+    const int total = sequence_grid();
+    // as many sequences per launch as still leave every sequence enough CTAs for the kernel's pixel sub-block limit
+    int per_launch = B;
+    while (per_launch > 1) {
+        const int g = total / per_launch;
+        if (g >= 1 && ((long long)((hw + g - 1) / g) + SEQ_NT - 1) / SEQ_NT <= SEQ_MAX_ITERS) break;
+        per_launch--;
+    }
+    const int g1 = total > 0 ? total / per_launch : 0;
+    const bool coop = total > 0 && g1 >= 1 && g1 <= 2048 && capacity < 0xffffffffll &&
+                      ((long long)((hw + g1 - 1) / g1) + SEQ_NT - 1) / SEQ_NT <= SEQ_MAX_ITERS;
+    unsigned char *w = (unsigned char *)workspace;
+    SeqParams *dev_params = (SeqParams *)(w + (size_t)B * per_ws);
+    const size_t pstride = align256(sizeof(SeqParams));
+    for (int b0 = 0; b0 < B; b0 += per_launch) {
+        const int nb = (B - b0 < per_launch) ? B - b0 : per_launch;
+        for (int b = b0; b < b0 + nb; b++) {
+            const float *d_b = depth + (size_t)b * L * hw, *rgb_b = rgb + (size_t)b * L * hw * 3, *K_b = K + (size_t)b * 16, *po_b = poses + (size_t)b * L * 16;
+            float *pt_b = map_points + (size_t)b * capacity * 3, *nr_b = map_normals + (size_t)b * capacity * 3,
+                  *co_b = map_colors + (size_t)b * capacity * 3, *cc_b = map_ccount + (size_t)b * capacity;
+            void *ws_b = w + (size_t)b * per_ws;
+            if (!coop) {            // no cooperative launch available: sequences one after another through the single-sequence entry
+                if (int rc = e2e_fusion_sequence(d_b, rgb_b, K_b, po_b, L, H, W, sigma, dist_th, dot_th, pt_b, nr_b, co_b, cc_b, n_map + 2 * b, 0,
+                                                 capacity, ws_b, per_ws, stream)) return rc;
+                continue;
+            }
+            const SeqParams p = make_seq_params(d_b, rgb_b, K_b, po_b, L, H, W, sigma, dist_th, dot_th, pt_b, nr_b, co_b, cc_b, n_map + 2 * b,
+                                                capacity, ws_b);
+            if (cudaMemsetAsync(p.counts, 0, align256(8 * 4096) + 256, st) != cudaSuccess) return finish_launch("fusion_sequence_batch: memset");
+            if (cudaMemcpyAsync((unsigned char *)dev_params + (size_t)(b - b0) * sizeof(SeqParams), &p, sizeof(SeqParams), cudaMemcpyHostToDevice, st) !=
+                cudaSuccess) return finish_launch("fusion_sequence_batch: parameter upload");
+        }
+        if (!coop) continue;
+        (void)pstride;
+        const SeqParams *pp = dev_params;
+        void *args[] = {(void *)&pp};
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void *)fusion_sequence_batch_kernel, dim3(total / nb, nb), dim3(SEQ_NT), args, 0, st);
+        if (e != cudaSuccess) {
+            set_error("fusion_sequence_batch: cooperative launch failed: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return (int)e;
+        }
+        count_launch();
+        // the parameter blocks of this wave are read by the running kernel: the next wave's upload must wait for it
+        if (b0 + nb < B && cudaStreamSynchronize(st) != cudaSuccess) return finish_launch("fusion_sequence_batch: sync between waves");
+    }
+    return finish_launch("fusion_sequence_batch");
 }
 
 }  // extern "C"

@@ -250,6 +250,57 @@ static int check_ws(void *ws, size_t bytes, size_t need)
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-pixel minimum over up to 8 candidate loss maps + mean (train_depth.py:653-658: `torch.min(photmetric, dim=1)` then
+// `.mean()`): the min-reprojection / auto-masking objective.  Candidates are separate [B,1,H,W] maps (the per-source photometric
+// maps and the identity maps), so the reference's torch.cat is never materialised.  torch.min semantics: the FIRST minimal
+// candidate wins, a NaN candidate wins over everything after it is met.  The winning index is kept (uint8) for the backward pass,
+// which routes the upstream gradient to that candidate only.
+// ------------------------------------------------------------------------------------------------
+struct MinCands {
+    const float *p[8];
+    float *g[8];
+    int C;
+};
+
+__global__ void __launch_bounds__(RED_NT) min_composite_fwd_kernel(const MinCands c, long long n, unsigned char *index, double *partial)
+{
+    double acc[1] = {0.0};
+    for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT) {
+        float best = __ldg(c.p[0] + i);
+        int bi = 0;
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+            if (k < c.C) {
+                const float v = __ldg(c.p[k] + i);
+                if (!(best != best) && (v < best || v != v)) { best = v; bi = k; }
+            }
+        }
+        index[i] = (unsigned char)bi;
+        acc[0] += (double)best;
+    }
+    block_partials<1>(acc, partial);
+}
+
+__global__ void __launch_bounds__(RED_NT) min_composite_final_kernel(const double *partial, int nblk, double inv_n, float *loss)
+{
+    double t[1];
+    sum_partials<1>(partial, nblk, t);
+    if (threadIdx.x == 0) loss[0] = (float)(t[0] * inv_n);
+}
+
+__global__ void __launch_bounds__(RED_NT) min_composite_bwd_kernel(const MinCands c, long long n, const unsigned char *index,
+                                                                   const float *grad_loss, float scale)
+{
+    const float gs = scale * (grad_loss ? __ldg(grad_loss) : 1.0f);
+    for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT) {
+        const int bi = index[i];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < c.C && c.g[k]) c.g[k][i] = (k == bi) ? gs : 0.0f;
+    }
+}
+
 }  // namespace e2e
 
 using namespace e2e;
@@ -377,6 +428,36 @@ int e2e_geometric_bwd(const float *warped_depth, const float *interp_depth, cons
                                                                              grad_warped, grad_interp);
     count_launch();
     return finish_launch("geometric_bwd");
+}
+
+int e2e_min_composite_fwd(const float *const *candidates, int n_candidates, long long n, unsigned char *index, float *loss,
+                          void *workspace, size_t workspace_bytes, void *stream)
+{
+    E2E_REQUIRE(candidates && n_candidates >= 1 && n_candidates <= 8 && n > 0 && index && loss, "min_composite: bad arguments");
+    MinCands c = {};
+    c.C = n_candidates;
+    for (int k = 0; k < n_candidates; k++) {
+        E2E_REQUIRE(candidates[k], "min_composite: null candidate map");
+        c.p[k] = candidates[k];
+    }
+    const int blocks = red_blocks(n);
+    E2E_REQUIRE(workspace && workspace_bytes >= blocks * sizeof(double), "min_composite: workspace too small");
+    min_composite_fwd_kernel<<<blocks, RED_NT, 0, (cudaStream_t)stream>>>(c, n, index, (double *)workspace);
+    min_composite_final_kernel<<<1, RED_NT, 0, (cudaStream_t)stream>>>((const double *)workspace, blocks, 1.0 / (double)n, loss);
+    count_launch(2);
+    return finish_launch("min_composite_fwd");
+}
+
+int e2e_min_composite_bwd(const unsigned char *index, int n_candidates, long long n, const float *grad_loss, float *const *grad_candidates,
+                          void *stream)
+{
+    E2E_REQUIRE(index && grad_candidates && n_candidates >= 1 && n_candidates <= 8 && n > 0, "min_composite_bwd: bad arguments");
+    MinCands c = {};
+    c.C = n_candidates;
+    for (int k = 0; k < n_candidates; k++) c.g[k] = grad_candidates[k];
+    min_composite_bwd_kernel<<<red_blocks(n), RED_NT, 0, (cudaStream_t)stream>>>(c, n, index, grad_loss, (float)(1.0 / (double)n));
+    count_launch();
+    return finish_launch("min_composite_bwd");
 }
 
 }  // extern "C"

@@ -402,7 +402,10 @@ static int launch_bwd(const WPParams &p, dim3 grid, cudaStream_t st)
 {
     auto kern = warp_photo_bwd_kernel<MODE, CK, B_TH, B_TW, B_NT, NEED_GY, IL>;
     constexpr size_t smem = bwd_smem_bytes<CK, NEED_GY>();
-    static bool configured = false;
+    static bool configured_dev[64] = {};          // per device (and per template instance): one process may drive several GPUs
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    bool &configured = configured_dev[dev_id & 63];
     if (!configured) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -28,6 +28,8 @@ struct WPParams {
     float *gP_partial;
     float *g_x, *g_y;
     const float *skip_flag;    // backward kernels return at once when *skip_flag != 0 (conditional backward)
+    int disp_mode;             // streaming kernel: `depth` holds the network's DISPARITY; depth = (1 / disp) * ratio is formed at the load
+    const float *ratio;        //   device scalar of the median scaling (online_adaption.py:295-298), NULL = none
 };
 
 // Per-CTA image handle: batch offset applied, 32-bit element strides (host checks they fit).

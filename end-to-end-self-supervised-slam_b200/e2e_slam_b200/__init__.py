@@ -10,9 +10,9 @@ The compute is in ../csrc (CUDA, C ABI in include/e2e_slam_b200.h); this package
 """
 from . import _lib  # noqa: F401
 from . import losses, ops, slam, view_synthesis  # noqa: F401
-from .ops import WarpPhotoPlan, photometric_map, ssim_map, warp_photometric, warp_photometric_loss  # noqa: F401
+from .ops import WarpPhotoPlan, photometric_map, ssim_map, warp_photometric, warp_photometric_loss, warp_photometric_multi  # noqa: F401
 from .slam import PointFusion, Pointclouds, RGBDImages, image_recover_slam, transform_pointcloud  # noqa: F401
 
-__all__ = ["warp_photometric", "warp_photometric_loss", "ssim_map", "photometric_map", "WarpPhotoPlan",
+__all__ = ["warp_photometric", "warp_photometric_loss", "warp_photometric_multi", "ssim_map", "photometric_map", "WarpPhotoPlan",
            "PointFusion", "Pointclouds", "RGBDImages", "image_recover_slam", "transform_pointcloud",
            "losses", "ops", "slam", "view_synthesis"]

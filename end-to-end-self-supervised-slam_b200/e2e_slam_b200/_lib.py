@@ -26,10 +26,13 @@ _SIGNATURES = {
     "e2e_warp_photo_bwd": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _F, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_warp_photo_vg_workspace_bytes": (_SZ, [_I, _I, _I]),
     "e2e_warp_photo_vg": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
+    "e2e_warp_photo_vg_disp": (_I, [_P, _P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_scale_by_scalar": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _P]),
     "e2e_u8_to_unit": (_I, [_P, _LL, _P, _P]),
     "e2e_disp_to_depth_fwd": (_I, [_P, _P, _LL, _P, _P]),
     "e2e_disp_to_depth_bwd": (_I, [_P, _P, _P, _LL, _P, _P]),
+    "e2e_select_workspace_bytes": (_SZ, []),
+    "e2e_select_kth": (_I, [_P, _LL, _LL, _P, _P, _SZ, _P]),
     "e2e_dual_disparity_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "e2e_dual_disparity_bwd": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "e2e_warp_photo_bwd_cond": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
@@ -56,6 +59,8 @@ _SIGNATURES = {
     "e2e_depth_reg_bwd": (_I, [_P, _P, _LL, _I, _P, _P, _P]),
     "e2e_geometric_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
     "e2e_geometric_bwd": (_I, [_P, _P, _P, _LL, _P, _P, _P, _P, _P]),
+    "e2e_min_composite_fwd": (_I, [_P, _I, _LL, _P, _P, _P, _SZ, _P]),
+    "e2e_min_composite_bwd": (_I, [_P, _I, _LL, _P, _P, _P]),
     "e2e_rgbd_maps": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     "e2e_rgbd_maps_bwd": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     "e2e_fusion_associate": (_I, [_P, _P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P]),
@@ -71,6 +76,8 @@ _SIGNATURES = {
     "e2e_icp_point_to_plane": (_I, [_P, _LL, _P, _P, _LL, _P, _I, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P, _SZ, _P]),
     "e2e_fusion_sequence_workspace_bytes": (_SZ, [_I, _I, _LL]),
     "e2e_fusion_sequence": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _LL, _LL, _P, _SZ, _P]),
+    "e2e_fusion_sequence_batch_workspace_bytes": (_SZ, [_I, _I, _I, _LL]),
+    "e2e_fusion_sequence_batch": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _LL, _P, _SZ, _P]),
     "e2e_fusion_merge_append_bwd": (_I, [_P] * 11 + [_I, _I] + [_P] * 7),
     "e2e_knn1_fwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P]),
     "e2e_knn1_bwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P]),

@@ -48,8 +48,24 @@ class FlatGradBucket:
             yield p, self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+    def adopt_grads(self):
+        """Make every member's `.grad` a view INTO the flat bucket (what DDP calls gradient_as_bucket_view): backward then
+        accumulates straight into the bucket and start() / finish() move no bytes except the all-reduce itself.  Existing
+        gradients are copied in once."""
+        for p, v in self._views():
+            if p.grad is not None:
+                v.copy_(p.grad)
+            else:
+                v.zero_()
+            p.grad = v
+        return self
+
+    def _is_view(self, p, v):
+        return p.grad is not None and p.grad.data_ptr() == v.data_ptr() and p.grad.shape == v.shape
+
     def start(self):
-        """Pack the gradients and launch the all-reduce (asynchronously on the side stream on GPUs)."""
+        """Launch the all-reduce(mean) (asynchronously on the side stream on GPUs); gradients that are not bucket views are
+        packed first.  NCCL averages inside the collective (ReduceOp.AVG); gloo sums and the division follows."""
         world = dist.get_world_size(self.group)
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -58,22 +74,29 @@ class FlatGradBucket:
             ctx = torch.autograd.profiler.record_function("e2e.bucket")
         with ctx:
             for p, v in self._views():
+                if self._is_view(p, v):
+                    continue
                 if p.grad is None:
                     v.zero_()
                 else:
                     v.copy_(p.grad)
-            self.flat.div_(world)
-            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if self.device.type == "cuda":
+                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            else:
+                self.flat.div_(world)
+                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         return self
 
     def finish(self):
-        """Wait for the all-reduce and scatter the averaged gradients back into `.grad`."""
+        """Wait for the all-reduce and hand the averaged gradients back (no copy for gradients that are bucket views)."""
         if self._work is None:
             raise RuntimeError("finish() called before start()")
         self._work.wait()
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         for p, v in self._views():
+            if self._is_view(p, v):
+                continue
             if p.grad is None:
                 p.grad = v.clone()
             else:

@@ -5,6 +5,7 @@ behaviour, backed by the CUDA kernels (no chamferdist / matplotlib imports neede
     geometric_consistency_loss, knn_points_loss, color_points_loss, depth_metrics, compute_depth_errors
 plus `smoothness_loss(disp, img)`, the fused form of compute_smoothness_loss (train_depth.py:763-773).
 """
+import ctypes
 import os
 
 import torch
@@ -229,6 +230,76 @@ def depth_metrics(dataset, gt, pred):
     else:
         raise ValueError("Dataset Not Found")
     return compute_depth_errors(gt[valid], pred[valid])
+
+
+# ------------------------------------------------------------------------------------------------
+# Multi-source photometric objective: mean over frames, min-reprojection, auto-masking (train_depth.py:615-660)
+# ------------------------------------------------------------------------------------------------
+class _MinComposite(torch.autograd.Function):
+    """mean over pixels of the per-pixel minimum over the candidate maps (`torch.min(photmetric, dim=1)` then `.mean()`,
+    train_depth.py:657-658), without materialising the reference's torch.cat; backward routes 1/n to the winning candidate."""
+
+    @staticmethod
+    def forward(ctx, *cands):
+        c0 = cands[0]
+        maps = [f32(c, "candidate map").contiguous() for c in cands]
+        if any(m.shape != c0.shape for m in maps):
+            raise ValueError("candidate maps must have equal shapes")
+        if not (1 <= len(maps) <= 8):
+            raise ValueError("between 1 and 8 candidate maps are supported")
+        n = c0.numel()
+        dev = c0.device
+        index = torch.empty(n, dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        nws = lib().e2e_reduce_workspace_bytes(n)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        arr = (ctypes.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+        with torch.cuda.device(dev):
+            check(lib().e2e_min_composite_fwd(arr, len(maps), n, ptr(index), ptr(loss), ptr(ws), nws, stream_ptr()), "e2e_min_composite_fwd")
+        ctx.save_for_backward(index)
+        ctx.shape, ctx.k = c0.shape, len(maps)
+        ctx.mark_non_differentiable(index)
+        return loss.reshape(()), index.view(c0.shape)
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (index,) = ctx.saved_tensors
+        g = f32(g, "grad").reshape(1).contiguous()
+        grads = [torch.empty(ctx.shape, dtype=torch.float32, device=index.device) if ctx.needs_input_grad[k] else None for k in range(ctx.k)]
+        arr = (ctypes.c_void_p * ctx.k)(*[0 if t is None else t.data_ptr() for t in grads])
+        with torch.cuda.device(index.device):
+            check(lib().e2e_min_composite_bwd(ptr(index), ctx.k, index.numel(), ptr(g), arr, stream_ptr()), "e2e_min_composite_bwd")
+        return tuple(grads)
+
+
+def photometric_objective(photometric_maps, identity_maps=None, min_reprojection=False, noise=None, return_index=False):
+    """The scalar the reference optimises from the per-source-frame photometric maps (compute_losses, train_depth.py:621-660):
+        photometric_maps   list of S maps (B,1,H,W) -- compute_photometric_loss, :707-727
+        identity_maps      list of S maps of the UN-warped source (compute_automasking_loss, :729-750) when LOSS.auto_masking
+        min_reprojection   LOSS.min_reprojection: keep the S maps as separate candidates instead of averaging them (:624-629)
+        noise              (B,S,H,W) tie-breaking noise added to the identity maps under min_reprojection (:646); the reference draws
+                           torch.randn(...) * 1e-5 on the spot -- pass it in for reproducibility (default: drawn here)
+    One candidate -> its mean; several -> mean of the per-pixel minimum (one kernel, e2e_min_composite_fwd)."""
+    maps = list(photometric_maps)
+    if not maps:
+        raise ValueError("no photometric maps")
+    cands = maps if min_reprojection else [maps[0] if len(maps) == 1 else torch.cat(maps, 1).mean(1, keepdim=True)]
+    if identity_maps is not None:
+        ident = list(identity_maps)
+        if len(ident) != len(maps):
+            raise ValueError("one identity map per source frame is required")
+        if min_reprojection:
+            if noise is None:
+                noise = torch.randn(maps[0].shape[0], len(ident), *maps[0].shape[2:], device=maps[0].device) * 0.00001
+            ident = [m + noise[:, s:s + 1] for s, m in enumerate(ident)]
+        else:
+            ident = [ident[0] if len(ident) == 1 else torch.cat(ident, 1).mean(1, keepdim=True)]
+        cands = ident + cands                                  # torch.cat((auto_masking, photmetric), dim=1), :651
+    if len(cands) == 1:
+        loss, index = cands[0].mean(), None
+    else:
+        loss, index = _MinComposite.apply(*cands)
+    return (loss, index) if return_index else loss
 
 
 # ------------------------------------------------------------------------------------------------

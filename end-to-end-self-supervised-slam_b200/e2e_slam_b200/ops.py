@@ -253,6 +253,71 @@ class _WarpPhotometricMean(torch.autograd.Function):
         return (grad_depth if need_depth else None, None, grad_K, grad_T, grad_src, None, None, None, None)
 
 
+class _WarpPhotometricMeanDisp(torch.autograd.Function):
+    """_WarpPhotometricMean fed with the depth network's disparity: depth = (1 / disp) * ratio is formed inside the sweep's depth
+    load and d loss / d disp comes back directly (e2e_warp_photo_vg_disp) -- no depth tensor, no separate elementwise passes."""
+
+    @staticmethod
+    def forward(ctx, disp, ratio, inv_K, K, T, src, tgt, padding_mode, use_mask, eps):
+        f32(disp, "disp"), f32(src, "source frame"), f32(tgt, "target frame")
+        if disp.dim() != 4 or disp.shape[1] != 1:
+            raise ValueError(f"disp must be (B,1,H,W), got {tuple(disp.shape)}")
+        B, _, H, W = disp.shape
+        if tuple(src.shape) != (B, 3, H, W) or tuple(tgt.shape) != (B, 3, H, W):
+            raise ValueError(f"source/target frames must be ({B},3,{H},{W}), got {tuple(src.shape)} / {tuple(tgt.shape)}")
+        if ratio is not None and ctx.needs_input_grad[1]:
+            raise NotImplementedError("the median-scaling ratio is a constant of this op, like the reference's in-place `*= ratio`")
+        disp_c = disp.contiguous()
+        r = None if ratio is None else f32(ratio, "ratio").detach().reshape(1).contiguous()
+        inv_K_c, K_c, T_c = _mat44(inv_K, B, "inv_K"), _mat44(K, B, "K"), _mat44(T, B, "T")
+        prepare_divisors(W - 1, H - 1, 9.0, 3.0)
+        dev = disp.device
+        need_src, need_K, need_T = ctx.needs_input_grad[5], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        n = lib().e2e_warp_photo_vg_workspace_bytes(B, H, W)
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad_disp = torch.empty_like(disp_c)
+        grad_src = torch.zeros(B, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
+        grad_P = torch.empty(B, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
+        with torch.cuda.device(dev):
+            rc = lib().e2e_warp_photo_vg_disp(ptr(disp_c), ptr(r), ptr(inv_K_c), ptr(K_c), ptr(T_c), ptr(src), strides4(src),
+                                              ptr(tgt), strides4(tgt), B, H, W, _pad_code(padding_mode), int(bool(use_mask)),
+                                              ctypes.c_float(eps), ptr(loss), ptr(grad_disp), ptr(grad_src),
+                                              strides4(grad_src) if grad_src is not None else None, ptr(grad_P), ptr(ws), n, stream_ptr())
+        check(rc, "e2e_warp_photo_vg_disp")
+        ctx.grads = (grad_disp, grad_src, grad_P)
+        ctx.save_for_backward(K_c, T_c)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grads is None:
+            raise RuntimeError("the gradients of this op are evaluated in the forward sweep and handed out once")
+        grad_disp, grad_src, grad_P = ctx.grads
+        ctx.grads = None
+        K, T = ctx.saved_tensors
+        g = f32(g, "grad").reshape(1).contiguous()
+        with torch.cuda.device(grad_disp.device):
+            check(lib().e2e_scale_by_scalar(ptr(grad_disp), grad_disp.numel(), ptr(grad_src), grad_src.numel() if grad_src is not None else 0,
+                                            ptr(grad_P), grad_P.numel() if grad_P is not None else 0, ptr(g), stream_ptr()), "e2e_scale_by_scalar")
+        grad_K = grad_T = None
+        if grad_P is not None:
+            if ctx.needs_input_grad[4]:
+                grad_T = torch.matmul(K[:, :3, :].transpose(1, 2), grad_P)
+            if ctx.needs_input_grad[3]:
+                grad_K = torch.zeros_like(K)
+                grad_K[:, :3, :] = torch.matmul(grad_P, T.transpose(1, 2))
+        return (grad_disp if ctx.needs_input_grad[0] else None, None, None, grad_K, grad_T, grad_src, None, None, None, None)
+
+
+def warp_photometric_loss_from_disparity(disp, inv_K, K, T, source_frame, target_frame, ratio=None, padding_mode="border",
+                                         photometric_mask=True, eps=1e-7):
+    """`warp_photometric_loss(1 / disp * ratio, ...)` with the conversion folded into the kernel (SURVEY.md 8(f) rank 2;
+    online_adaption.py:282-298): `disp` (B,1,H,W) is the network's output, `ratio` the 0-dim device tensor of the median scaling
+    (ops.median_ratio) or None.  Bit-identical loss, gradient w.r.t. the disparity returned directly."""
+    return _WarpPhotometricMeanDisp.apply(disp, ratio, inv_K, K, T, source_frame, target_frame, padding_mode, photometric_mask, eps)
+
+
 def warp_photometric(depth, inv_K, K, T, source_frame, target_frame, padding_mode="border",
                      photometric_mask=True, need_outputs=False, eps=1e-7):
     """Per-pixel photometric loss of warping `source_frame` into the target view.
@@ -270,6 +335,32 @@ def warp_photometric_loss(depth, inv_K, K, T, source_frame, target_frame, paddin
     neither the synthesized frame nor the loss map is written to memory."""
     return _WarpPhotometricMean.apply(depth, inv_K, K, T, source_frame, target_frame, padding_mode,
                                       photometric_mask, eps)
+
+
+def warp_photometric_multi(depth, inv_K, K, transforms, source_frames, target_frame, padding_mode="border", photometric_mask=True,
+                           min_reprojection=False, auto_masking=False, noise=None, eps=1e-7):
+    """The reference's whole photometric objective for S source frames per target (novel_view_synthesis + compute_photometric_loss +
+    compute_automasking_loss + the frame reduction of compute_losses; train_depth.py:545-613, 615-660, 707-750): one fused sweep per
+    source frame (loss map + validity mask), the identity maps of the un-warped sources through the stand-alone SSIM kernel when
+    `auto_masking`, and the mean / per-pixel-minimum reduction (losses.photometric_objective).  Returns the scalar loss;
+    differentiable w.r.t. depth, the poses and the source frames.  With the plain mean (the shipped default) the upstream gradient
+    of every map is uniform and the gradients come from the forward sweeps; under min-reprojection / auto-masking the per-pixel
+    selection makes it non-uniform and each source frame's streaming backward kernel runs with the selection mask."""
+    from . import losses
+    if len(transforms) != len(source_frames) or not transforms:
+        raise ValueError("one transform per source frame is required")
+    maps, ident = [], []
+    for T, src in zip(transforms, source_frames):
+        if auto_masking:
+            lm, _, valid, _ = warp_photometric(depth, inv_K, K, T, src, target_frame, padding_mode, photometric_mask, True, eps)
+            if photometric_mask:                                  # train_depth.py:736-742
+                ident.append(photometric_map(src * valid, target_frame * valid))
+            else:
+                ident.append(photometric_map(src, target_frame))
+        else:
+            lm = warp_photometric(depth, inv_K, K, T, src, target_frame, padding_mode, photometric_mask, False, eps)
+        maps.append(lm)
+    return losses.photometric_objective(maps, ident if auto_masking else None, min_reprojection, noise)
 
 
 class _SSIM(torch.autograd.Function):
@@ -362,6 +453,35 @@ def disp_to_depth(disp, ratio=None):
     """depth = 1 / disp, optionally times the median-scaling ratio (a 0-dim device tensor, treated as a constant like the
     reference's in-place `*= ratio`): online_adaption.py:282, 295-298; train_depth.py:323-340.  One kernel each way."""
     return _DispToDepth.apply(disp, ratio)
+
+
+def select_kth(x, k):
+    """k-th smallest (0-based) element of a CUDA fp32 tensor as a 0-dim device tensor: radix select, no sort, no host sync."""
+    f32(x, "x")
+    flat = x.contiguous().view(-1)
+    n = flat.numel()
+    if not (0 <= k < n):
+        raise IndexError(f"rank {k} out of range for {n} elements")
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    nws = lib().e2e_select_workspace_bytes()
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().e2e_select_kth(ptr(flat), n, k, ptr(out), ptr(ws), nws, stream_ptr()), "e2e_select_kth")
+    return out.reshape(())
+
+
+def median(x):
+    """torch.median(x) over all elements (the lower median, NaN if any NaN) without torch's sort."""
+    return select_kth(x, (x.numel() - 1) // 2)
+
+
+def median_ratio_from_disparity(gt_depths, disps):
+    """The reference's median scaling `ratio = torch.median(gt_depths) / torch.median(depth_tensor)` (online_adaption.py:295) with
+    depth_tensor = 1 / disps never materialised: for positive disparities the lower median of 1/disp is exactly 1 / (the n/2-th
+    smallest disparity).  Returns a 0-dim device tensor (a constant, like the reference's in-place `*= ratio`)."""
+    with torch.no_grad():
+        d = disps.detach()
+        return median(gt_depths.detach()) / (1.0 / select_kth(d, d.numel() // 2))
 
 
 def _row_mask(H, device):

@@ -388,32 +388,41 @@ class PointFusion:
         return out, poses
 
     def _fuse_sequence(self, frames):
-        """Known poses, no autograd: the frame loop runs inside the library (e2e_fusion_sequence), one call per batch
-        element, instead of ~15 launches / memsets / allocations per frame from Python."""
+        """Known poses, no autograd: the frame loop runs inside the library -- e2e_fusion_sequence for one sequence, ONE
+        cooperative launch over all B sequences (e2e_fusion_sequence_batch) for a batch -- instead of ~15 launches / memsets /
+        allocations per frame and batch element from Python."""
         B, L, H, W = frames.shape[:4]
         dev = frames.device
         out = Pointclouds(device=dev)
         maps = []
+        cap = L * H * W
+        z = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            for b in range(B):
-                depth = f32(frames.depth_image[b, :, :, :, 0], "depth_image").contiguous()
-                rgb = f32(frames.rgb_image[b], "rgb_image").contiguous()
-                K = f32(frames.intrinsics[b, 0], "intrinsics").contiguous()
-                poses = f32(frames.poses[b], "poses").contiguous()
-                cap = L * H * W
-                z = dict(dtype=torch.float32, device=dev)
-                pts, nrm, col, cc = torch.empty(cap, 3, **z), torch.empty(cap, 3, **z), torch.empty(cap, 3, **z), torch.empty(cap, **z)
-                n = torch.zeros(2, dtype=torch.int64, device=dev)
+            depth = f32(frames.depth_image[..., 0], "depth_image").contiguous()
+            rgb = f32(frames.rgb_image, "rgb_image").contiguous()
+            K = f32(frames.intrinsics[:, 0], "intrinsics").contiguous()
+            poses = f32(frames.poses, "poses").contiguous()
+            pts, nrm, col, cc = torch.empty(B, cap, 3, **z), torch.empty(B, cap, 3, **z), torch.empty(B, cap, 3, **z), torch.empty(B, cap, **z)
+            n = torch.zeros(B, 2, dtype=torch.int64, device=dev)
+            if B == 1:
                 nws = lib().e2e_fusion_sequence_workspace_bytes(H, W, cap)
                 ws = torch.empty(nws, dtype=torch.uint8, device=dev)
                 check(lib().e2e_fusion_sequence(ptr(depth), ptr(rgb), ptr(K), ptr(poses), L, H, W, ctypes.c_float(self.sigma),
                                                 ctypes.c_float(self.dist_th), ctypes.c_float(self.dot_th), ptr(pts), ptr(nrm),
                                                 ptr(col), ptr(cc), ptr(n), 0, cap, ptr(ws), nws, stream_ptr()),
                       "e2e_fusion_sequence")
-                m = _Map(dev)
-                m.pts, m.nrm, m.col, m.cc, m.n_dev = pts, nrm, col, cc, n[:1]
-                m.n_upper, m.n_host = cap, 0
-                maps.append(m)
+            else:
+                nws = lib().e2e_fusion_sequence_batch_workspace_bytes(B, H, W, cap)
+                ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+                check(lib().e2e_fusion_sequence_batch(ptr(depth), ptr(rgb), ptr(K), ptr(poses), B, L, H, W, ctypes.c_float(self.sigma),
+                                                      ctypes.c_float(self.dist_th), ctypes.c_float(self.dot_th), ptr(pts), ptr(nrm),
+                                                      ptr(col), ptr(cc), ptr(n), cap, ptr(ws), nws, stream_ptr()),
+                      "e2e_fusion_sequence_batch")
+        for b in range(B):
+            m = _Map(dev)
+            m.pts, m.nrm, m.col, m.cc, m.n_dev = pts[b], nrm[b], col[b], cc[b], n[b, :1]
+            m.n_upper, m.n_host = cap, 0
+            maps.append(m)
         out._maps = maps
         self.last_association = []
         return out

@@ -110,6 +110,16 @@ int e2e_warp_photo_vg(const float *depth, const float *inv_K, const float *K, co
                       float *loss_mean, float *grad_depth, float *grad_src, const int64_t grad_src_strides[4],
                       float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same sweep fed with the depth network's DISPARITY (online_adaption.py:282, 295-298): depth =
+ * (1 / disp) * ratio is formed at the kernel's depth load (ratio = device scalar of the median scaling, NULL = none; reciprocal and
+ * scaling are two roundings as in the reference, so the loss is bit-identical to e2e_disp_to_depth_fwd + e2e_warp_photo_vg) and
+ * grad_disp = d loss / d disp comes back directly. */
+int e2e_warp_photo_vg_disp(const float *disp, const float *ratio, const float *inv_K, const float *K, const float *T,
+                           const float *src, const int64_t src_strides[4], const float *tgt, const int64_t tgt_strides[4],
+                           int B, int H, int W, int padding_mode, int use_mask, float eps,
+                           float *loss_mean, float *grad_disp, float *grad_src, const int64_t grad_src_strides[4],
+                           float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
+
 /* The same sweep with the forward tensors the reference's scripts keep (train_depth.py:581-590, 726) as outputs: loss_map
  * [B,1,H,W] (bit-exact, like e2e_warp_photo_fwd), syn [B,3,H,W], valid [B,1,H,W], pix [B,H,W,2]; each nullable, at least one
  * required; loss_mean nullable.  The gradients are those of mean(loss_map), i.e. of an upstream gradient 1/(B*H*W) at every
@@ -215,6 +225,16 @@ int e2e_geometric_fwd(const float *warped_depth, const float *interp_depth, cons
 int e2e_geometric_bwd(const float *warped_depth, const float *interp_depth, const float *valid, long long n, const float *mask_sum,
                       const float *grad_loss, float *grad_warped, float *grad_interp, void *stream);
 
+/* Min-reprojection / auto-masking objective (train_depth.py:642-658): loss = mean over pixels of the per-pixel MINIMUM over
+ * n_candidates (<= 8) loss maps of n = B*H*W values each (`candidates` / `grad_candidates` are HOST arrays of device pointers; the
+ * reference's torch.cat is never materialised).  torch.min semantics: first minimal candidate wins, NaN propagates.  `index`
+ * (uint8 [n]) receives the winner; the backward pass writes grad_loss / n into the winner's map and 0 into the others
+ * (NULL entries of grad_candidates are skipped). */
+int e2e_min_composite_fwd(const float *const *candidates, int n_candidates, long long n, unsigned char *index, float *loss,
+                          void *workspace, size_t workspace_bytes, void *stream);
+int e2e_min_composite_bwd(const unsigned char *index, int n_candidates, long long n, const float *grad_loss,
+                          float *const *grad_candidates, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * PointFusion (gradslam semantics; gradslam itself is not vendored by the
  * reference -- call sites slam/custom_slam.py:33, online_adaption.py:354-363, 466-469, train_depth.py:266).
@@ -280,6 +300,17 @@ int e2e_fusion_sequence(const float *depth, const float *rgb, const float *K, co
                         long long *n_map, long long n_upper, long long capacity,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* B independent sequences of equal shape in ONE cooperative launch (gradslam's batch dimension: train_depth.py:263-267): grid =
+ * (CTAs per sequence, B), every sequence with its own barrier and working buffers, so the sequences fill each other's dependent-
+ * round-trip and barrier bubbles.  Layouts: depth [B,L,H,W], rgb [B,L,H,W,3], K [B,4,4], poses [B,L,4,4]; map arrays [B,capacity,3]
+ * / [B,capacity], maps start empty; n_map int64 [B,2] (zero-filled by the caller; n_map[b][0] receives the point count).  If B
+ * exceeds what one launch can co-schedule the batch runs in waves. */
+size_t e2e_fusion_sequence_batch_workspace_bytes(int B, int H, int W, long long capacity);
+int e2e_fusion_sequence_batch(const float *depth, const float *rgb, const float *K, const float *poses, int B, int L, int H, int W,
+                              float sigma, float dist_th, float dot_th,
+                              float *map_points, float *map_normals, float *map_colors, float *map_ccount,
+                              long long *n_map, long long capacity, void *workspace, size_t workspace_bytes, void *stream);
+
 int e2e_fusion_merge_append_bwd(const float *grad_points, const float *grad_colors, const float *grad_ccount,
                                 const float *old_points, const float *old_colors, const float *old_ccount,
                                 const float *vertex_g, const float *rgb, const float *alpha,
@@ -343,6 +374,13 @@ int e2e_icp_point_to_plane(const float *src, long long N, const float *tgt, cons
                            const float *T_init, int numiters, float damp, float dist_thresh,
                            int grad_icp, float lambda_max, float B, float B2, float nu,
                            float *T_out, long long *idx_out, float *errs, void *workspace, size_t workspace_bytes, void *stream);
+
+/* k-th smallest (0-based) of n fp32 values by radix select: four rounds of an 8-bit histogram + pick, nothing is sorted and the host
+ * is never synchronised.  torch.median(x) (online_adaption.py:295) is k = (n-1)/2; a NaN anywhere gives NaN, as torch does.
+ * median(1 / disp) of a positive disparity map is 1 / (the n/2-th smallest disparity) exactly (x -> RN(1/x) is monotone), so the
+ * median-scaling ratio needs no materialised depth. */
+size_t e2e_select_workspace_bytes(void);
+int e2e_select_kth(const float *x, long long n, long long k, float *out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The elementwise passes next to the depth network.

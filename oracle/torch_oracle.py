@@ -18,6 +18,7 @@ Reference lines restated (paths relative to the reference repo root):
   ssim                   loss/losses.py:23-37
   photometric            loss/losses.py:97-117
   frames mean / min      train_depth.py:629, 657-660
+  min-reprojection, auto-masking objective   train_depth.py:615-660, 729-750
   smoothness             train_depth.py:763-773 + loss/losses.py:119-132
   sparse gt L1           loss/losses.py:151-160
   depth regulariser      loss/losses.py:134-148
@@ -60,7 +61,7 @@ def project(points, K, T, H, W, eps=1e-7, geometric=False):
     return pix, valid
 
 
-def ssim(x, y):
+def ssim(x, y, return_raw=False):
     x = F.pad(x, (1, 1, 1, 1), mode="reflect")                  # losses.py:24-25
     y = F.pad(y, (1, 1, 1, 1), mode="reflect")
     mu_x = F.avg_pool2d(x, 3, 1)                                # :27-28
@@ -70,7 +71,10 @@ def ssim(x, y):
     sig_xy = F.avg_pool2d(x * y, 3, 1) - mu_x * mu_y
     n = (2 * mu_x * mu_y + C1) * (2 * sig_xy + C2)              # :34
     d = (mu_x ** 2 + mu_y ** 2 + C1) * (sig_x + sig_y + C2)     # :35
-    return torch.clamp((1 - n / d) / 2, 0, 1)                   # :37
+    raw = (1 - n / d) / 2
+    if return_raw:                                              # the value BEFORE the clamp (tests use it to find clamp kinks)
+        return raw
+    return torch.clamp(raw, 0, 1)                               # :37
 
 
 def photometric(pred, target):
@@ -100,6 +104,28 @@ def photometric_total(depth, inv_K, K, Ts, srcs, tgt, padding_mode="border", use
     if min_reprojection and maps.shape[1] > 1:
         return torch.min(maps, dim=1)[0].mean()
     return maps.mean(1, keepdim=True).mean()
+
+
+def photometric_objective(depth, inv_K, K, Ts, srcs, tgt, padding_mode="border", use_mask=True, min_reprojection=False,
+                          auto_masking=False, noise=None):
+    """compute_losses with compute_photometric_loss / compute_automasking_loss (train_depth.py:615-660, 707-750) for S source frames:
+    returns (scalar, index of the winning candidate per pixel or None).  `noise` (B,S,H,W) is the tie-breaking term of :646."""
+    maps, ident = [], []
+    for T, s in zip(Ts, srcs):
+        lm, _, valid, _ = warp_photometric(depth, inv_K, K, T, s, tgt, padding_mode, use_mask)
+        maps.append(lm)
+        ident.append(photometric(s * valid, tgt * valid) if use_mask else photometric(s, tgt))     # :736-747
+    photo = torch.cat(maps, 1)                                  # :726
+    if not min_reprojection:
+        photo = photo.mean(1, keepdim=True)                     # :629
+    if auto_masking:
+        am = torch.cat(ident, 1)                                # :749
+        am = am + noise if min_reprojection else am.mean(1, keepdim=True)     # :645-649
+        photo = torch.cat((am, photo), dim=1)                   # :651
+    if photo.shape[1] == 1:
+        return photo.mean(), None                               # :653-655
+    v, i = torch.min(photo, dim=1)                              # :657
+    return v.mean(), i
 
 
 def smoothness(disp, img):

@@ -19,11 +19,21 @@ def pytest_configure(config):
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Single-source goldens of tools/make_golden.py (the composite_* files of tools/make_golden_composite.py have their own fixture)."""
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("composite_"))
+
+
+def composite_golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "composite_*.npz")))
 
 
 @pytest.fixture(params=golden_files(), ids=lambda p: os.path.basename(p)[:-4])
 def golden(request):
+    return np.load(request.param)
+
+
+@pytest.fixture(params=composite_golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def composite_golden(request):
     return np.load(request.param)
 
 

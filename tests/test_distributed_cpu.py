@@ -57,6 +57,24 @@ def _worker(rank, world, port, out):
     dist.all_gather_object(losses, float(loss))
     ok &= abs(float(m) - sum(losses) / world) < 1e-6
     ok &= bucket.numel == sum(p.numel() for p in net.parameters() if p.requires_grad)
+    # second step with the gradients living INSIDE the bucket (adopt_grads): backward accumulates into the views, the
+    # all-reduce moves no other bytes, and .grad must still alias the flat buffer afterwards
+    bucket.adopt_grads()
+    for p_ in net.parameters():
+        if p_.grad is not None:
+            p_.grad.zero_()
+    x2 = torch.randn(8, 6, generator=torch.Generator().manual_seed(200))
+    net[2](net[1](net[0](x2[mine]))).pow(2).mean().backward()
+    local2 = {n: p_.grad.clone() for n, p_ in net.named_parameters() if p_.requires_grad}
+    bucket.start().finish()
+    gathered2 = [None] * world
+    dist.all_gather_object(gathered2, local2)
+    lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + bucket.flat.numel() * 4
+    for n, p_ in net.named_parameters():
+        if not p_.requires_grad:
+            continue
+        ok &= lo <= p_.grad.data_ptr() < hi
+        ok &= torch.allclose(p_.grad, sum(g[n] for g in gathered2) / world, atol=1e-7)
     if rank == 0:
         out.put(bool(ok))
     dist.destroy_process_group()

@@ -1,6 +1,7 @@
 """CPU tests: the oracles against the golden vectors produced by the real reference
 (tools/make_golden.py).  These pin the oracles; the GPU tests then compare CUDA with them."""
 import numpy as np
+import pytest
 import torch
 
 from conftest import rel_max, same_values
@@ -72,3 +73,28 @@ def test_small_losses_oracle_vs_reference(golden):
         assert same_values(b.grad.numpy(), g["g_reg_" + kind]) == 0
     gl = torch_oracle.geometric_consistency(_t(g, "warped_depth"), _t(g, "interp_depth"), _t(g, "valid"))
     assert same_values(gl.numpy(), g["geo_loss"]) == 0
+
+
+@pytest.mark.parametrize("mr,am", [(False, False), (True, False), (False, True), (True, True)])
+def test_torch_oracle_multi_source_objective_matches_reference(composite_golden, mr, am):
+    """oracle/torch_oracle.photometric_objective (mean over frames / min-reprojection / auto-masking, train_depth.py:615-660, 729-750)
+    against goldens produced with the reference's own modules (tools/make_golden_composite.py): same winning candidate at every pixel,
+    same loss bit for bit, depth gradient to 1e-5 (the reference back-projects once for all source frames,
+    the oracle once per frame: autograd accumulates in a different order)."""
+    import torch
+    from oracle import torch_oracle as to
+    g = composite_golden
+    tag = f"mr{int(mr)}_am{int(am)}"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    depth = t(g["depth"]).requires_grad_(True)
+    colors = t(g["colors"])
+    S = g["T"].shape[1]
+    srcs = [colors[:, 1 + s].permute(0, 3, 1, 2) for s in range(S)]
+    torch.set_num_threads(1)                                   # the generator fixed torch's reduction tree the same way
+    loss, index = to.photometric_objective(depth, t(g["inv_K"]), t(g["K"]), [t(g["T"][:, s]) for s in range(S)], srcs,
+                                           colors[:, 0].permute(0, 3, 1, 2), str(g["padding_mode"]), bool(g["use_mask"]), mr, am, t(g["noise"]))
+    loss.backward()
+    if index is not None:
+        assert np.array_equal(index.numpy(), g[f"index_{tag}"])
+    assert float(loss) == float(g[f"loss_{tag}"])
+    assert rel_max(depth.grad.numpy(), g[f"g_depth_{tag}"]) <= 1e-5

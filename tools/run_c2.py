@@ -1,5 +1,5 @@
 import sys, json
 sys.path.insert(0, "/root/repo/end-to-end-self-supervised-slam_b200"); sys.path.insert(0, "/root/repo")
 import torch
-from e2e_slam_b200 import c2_bench
+from benchmarks import c2_bench
 print(json.dumps(c2_bench.run("cuda:0"), indent=1))

@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "end-to-end-self-supervised-slam_b200"))
 import torch  # noqa: E402
-from e2e_slam_b200 import fusion_bench  # noqa: E402
+from benchmarks import fusion_bench  # noqa: E402
 
 r = fusion_bench.run(torch.device("cuda", 0), repeats=5)
 print(json.dumps({k: r[k] for k in ("value", "ms_per_sequence", "final_map_points", "gpu_launches")} | {"frac": r["roofline"]["frac"],
