@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT) warp_photo_fwd_kernel(const __grid_constan
     const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
 
     if (MODE == MODE_WARP) {
-        stage_camera(p, b, cam);
+        stage_camera(p, b, b, cam);
         __syncthreads();
     }
     const bool bad = fill_region<MODE, CK, RH, RP, 1, TH, TW, IL>(p, cam, b, ch0, ty0, tx0, sx, sy, true);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(NT) warp_photo_bwd_kernel(const __grid_constan
     if (!p.g_loss_map && !p.g_ssim) gscal = (p.g_scalar ? __ldg(p.g_scalar) : 1.0f) * p.g_scale;
 
     if (MODE == MODE_WARP) {
-        stage_camera(p, b, cam);
+        stage_camera(p, b, b, cam);
         __syncthreads();
     }
     // ---- phase A ---------------------------------------------------------------------------

@@ -28,6 +28,8 @@ struct WPParams {
     float *gP_partial;
     float *g_x, *g_y;
     const float *skip_flag;    // backward kernels return at once when *skip_flag != 0 (conditional backward)
+    int S;                     // streaming kernel: source frames per target (0 / 1 = one).  blockIdx.z = pair * S + source: depth, target and
+                               //   intrinsics are indexed by the pair, pose / source image / every output by (pair, source)
     int disp_mode;             // streaming kernel: `depth` holds the network's DISPARITY; depth = (1 / disp) * ratio is formed at the load
     const float *ratio;        //   device scalar of the median scaling (online_adaption.py:295-298), NULL = none
 };
@@ -77,16 +79,17 @@ __device__ __forceinline__ bool value_out_of_fast_range(float v)
 // cam[9..20] = P = (K @ T)[:3, :] with the k-loop accumulated in order (unfused), like at::bmm's
 // small-matrix path (view_synthesis.py:57).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_camera(const WPParams &p, int b, float *cam)
+// bk = index of the intrinsics, bt = index of the pose (they differ when several source frames share a target)
+__device__ __forceinline__ void stage_camera(const WPParams &p, int bk, int bt, float *cam)
 {
     const int t = threadIdx.x;
     if (t < 9) {
-        cam[t] = p.inv_K[b * 16 + (t / 3) * 4 + (t % 3)];
+        cam[t] = p.inv_K[bk * 16 + (t / 3) * 4 + (t % 3)];
     } else if (t < 21) {
         const int e = t - 9, i = e >> 2, j = e & 3;
         float acc = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 4; k++) acc = xadd(acc, xmul(p.K[b * 16 + i * 4 + k], p.T[b * 16 + k * 4 + j]));
+        for (int k = 0; k < 4; k++) acc = xadd(acc, xmul(p.K[bk * 16 + i * 4 + k], p.T[bt * 16 + k * 4 + j]));
         cam[t] = acc;
     }
 }

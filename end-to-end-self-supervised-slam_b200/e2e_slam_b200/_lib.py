@@ -26,6 +26,8 @@ _SIGNATURES = {
     "e2e_warp_photo_bwd": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _F, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_warp_photo_vg_workspace_bytes": (_SZ, [_I, _I, _I]),
     "e2e_warp_photo_vg": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
+    "e2e_warp_photo_vg_multi_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "e2e_warp_photo_vg_multi": (_I, [_P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_warp_photo_vg_disp": (_I, [_P, _P, _P, _P, _P, _P, _S, _P, _S, _I, _I, _I, _I, _I, _F, _P, _P, _P, _S, _P, _P, _SZ, _P]),
     "e2e_scale_by_scalar": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _P]),
     "e2e_u8_to_unit": (_I, [_P, _LL, _P, _P]),

@@ -337,6 +337,78 @@ def warp_photometric_loss(depth, inv_K, K, T, source_frame, target_frame, paddin
                                       photometric_mask, eps)
 
 
+class _WarpPhotometricMeanMulti(torch.autograd.Function):
+    """S source frames per target in ONE sweep launch (e2e_warp_photo_vg_multi): loss = mean over frames and pixels
+    (`.mean(1, keepdim=True).mean()`, train_depth.py:629, 657) and all gradients, evaluated in forward()."""
+
+    @staticmethod
+    def forward(ctx, depth, inv_K, K, T, src, tgt, padding_mode, use_mask, eps):
+        f32(depth, "depth"), f32(src, "source frames"), f32(tgt, "target frame")
+        B, _, H, W = depth.shape
+        if src.dim() != 5 or src.shape[0] != B or tuple(src.shape[2:]) != (3, H, W) or tuple(tgt.shape) != (B, 3, H, W):
+            raise ValueError(f"expected sources ({B},S,3,{H},{W}) and target ({B},3,{H},{W}), got {tuple(src.shape)} / {tuple(tgt.shape)}")
+        S = src.shape[1]
+        if tuple(T.shape) != (B, S, 4, 4):
+            raise ValueError(f"transforms must be ({B},{S},4,4), got {tuple(T.shape)}")
+        if S > 1 and src.stride(0) != S * src.stride(1):          # (pair, source) must flatten to one strided axis
+            src = src.contiguous()
+        flat = src.flatten(0, 1) if S > 1 and src.stride(0) == S * src.stride(1) else src.reshape(B * S, 3, H, W)
+        depth_c = depth.contiguous()
+        inv_K_c, K_c = _mat44(inv_K, B, "inv_K"), _mat44(K, B, "K")
+        T_c = f32(T, "T").reshape(B * S, 4, 4).contiguous()
+        prepare_divisors(W - 1, H - 1, 9.0, 3.0)
+        dev = depth.device
+        need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
+        n = lib().e2e_warp_photo_vg_multi_workspace_bytes(B, S, H, W)
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad_depth = torch.empty_like(depth_c)
+        grad_src = torch.zeros(B * S, 3, H, W, dtype=torch.float32, device=dev) if need_src else None
+        grad_P = torch.empty(B * S, 3, 4, dtype=torch.float32, device=dev) if (need_K or need_T) else None
+        with torch.cuda.device(dev):
+            rc = lib().e2e_warp_photo_vg_multi(ptr(depth_c), ptr(inv_K_c), ptr(K_c), ptr(T_c), ptr(flat), strides4(flat), ptr(tgt),
+                                               strides4(tgt), B, S, H, W, _pad_code(padding_mode), int(bool(use_mask)), ctypes.c_float(eps),
+                                               ptr(loss), ptr(grad_depth), ptr(grad_src), strides4(grad_src) if grad_src is not None else None,
+                                               ptr(grad_P), ptr(ws), n, stream_ptr())
+        check(rc, "e2e_warp_photo_vg_multi")
+        ctx.grads = (grad_depth, grad_src, grad_P)
+        ctx.save_for_backward(K_c, T_c)
+        ctx.dims = (B, S, H, W)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grads is None:
+            raise RuntimeError("the gradients of this op are evaluated in the forward sweep and handed out once")
+        grad_depth, grad_src, grad_P = ctx.grads
+        ctx.grads = None
+        K, T = ctx.saved_tensors
+        B, S, H, W = ctx.dims
+        need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
+        g = f32(g, "grad").reshape(1).contiguous()
+        with torch.cuda.device(grad_depth.device):
+            check(lib().e2e_scale_by_scalar(ptr(grad_depth), grad_depth.numel(), ptr(grad_src), grad_src.numel() if grad_src is not None else 0,
+                                            ptr(grad_P), grad_P.numel() if grad_P is not None else 0, ptr(g), stream_ptr()), "e2e_scale_by_scalar")
+        grad_K = grad_T = None
+        if grad_P is not None:
+            Kr = K.repeat_interleave(S, 0)
+            if need_T:
+                grad_T = torch.matmul(Kr[:, :3, :].transpose(1, 2), grad_P).view(B, S, 4, 4)
+            if need_K:
+                grad_K = torch.zeros_like(K)
+                grad_K[:, :3, :] = torch.matmul(grad_P, T.transpose(1, 2)).view(B, S, 3, 4).sum(1)
+        return (grad_depth if need_depth else None, None, grad_K, grad_T,
+                grad_src.view(B, S, 3, H, W) if grad_src is not None else None, None, None, None, None)
+
+
+def warp_photometric_loss_multi(depth, inv_K, K, transforms, source_frames, target_frame, padding_mode="border", photometric_mask=True,
+                                eps=1e-7):
+    """Scalar photometric loss for S source frames per target -- `photometric_losses.mean(1, keepdim=True).mean()` of
+    train_depth.py:726, 629, 657 -- in ONE launch of the sweep (grid z = pair x source).  `transforms` (B,S,4,4); `source_frames`
+    (B,S,3,H,W), any inner strides (e.g. `colors[:, 1:].permute(0, 1, 4, 2, 3)` of channels-last memory goes in without a copy)."""
+    return _WarpPhotometricMeanMulti.apply(depth, inv_K, K, transforms, source_frames, target_frame, padding_mode, photometric_mask, eps)
+
+
 def warp_photometric_multi(depth, inv_K, K, transforms, source_frames, target_frame, padding_mode="border", photometric_mask=True,
                            min_reprojection=False, auto_masking=False, noise=None, eps=1e-7):
     """The reference's whole photometric objective for S source frames per target (novel_view_synthesis + compute_photometric_loss +

@@ -110,6 +110,17 @@ int e2e_warp_photo_vg(const float *depth, const float *inv_K, const float *K, co
                       float *loss_mean, float *grad_depth, float *grad_src, const int64_t grad_src_strides[4],
                       float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
 
+/* S source frames per target in ONE launch (`int S`; train_depth.py:545-613 loops over DATA.frames[1:]): the grid's z
+ * extent is (pair, source).  depth [B,1,H,W], inv_K / K [B,4,4] and tgt (B pairs) are indexed by the pair; T [B*S,4,4], src (a
+ * [B*S,3,H,W] view), grad_src [B*S,3,H,W] and grad_P [B*S,3,4] by (pair, source).  loss_mean = mean over the B*S*H*W per-frame loss
+ * values (= `.mean(1, keepdim=True).mean()`), grad_depth [B,1,H,W] = the sum over the pair's source frames (a second, tiny launch). */
+size_t e2e_warp_photo_vg_multi_workspace_bytes(int B, int S, int H, int W);
+int e2e_warp_photo_vg_multi(const float *depth, const float *inv_K, const float *K, const float *T,
+                            const float *src, const int64_t src_strides[4], const float *tgt, const int64_t tgt_strides[4],
+                            int B, int S, int H, int W, int padding_mode, int use_mask, float eps,
+                            float *loss_mean, float *grad_depth, float *grad_src, const int64_t grad_src_strides[4],
+                            float *grad_P, void *workspace, size_t workspace_bytes, void *stream);
+
 /* The same sweep fed with the depth network's DISPARITY (online_adaption.py:282, 295-298): depth =
  * (1 / disp) * ratio is formed at the kernel's depth load (ratio = device scalar of the median scaling, NULL = none; reciprocal and
  * scaling are two roundings as in the reference, so the loss is bit-identical to e2e_disp_to_depth_fwd + e2e_warp_photo_vg) and

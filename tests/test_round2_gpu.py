@@ -387,3 +387,67 @@ def test_graphed_refinement_step_matches_eager():
         assert rel_max(db.detach().cpu().numpy(), da.detach().cpu().numpy()) <= 1e-6, i
     assert graphed.graph is not None                 # steps 3.. were graph replays
     assert np.isfinite(float(ta["loss"]))
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 2, 2), (1, 3, 3), (1, 17, 5), (2, 48, 64), (1, 37, 52), (5, 96, 128)])
+def test_sweep_writes_stay_inside_its_buffers(B, H, W):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES of the streaming kernel (TMA and generic instances, tiny
+    and ragged shapes, row segments) are caught with canaries: every output / workspace buffer of WarpPhotoPlan is carved out of one
+    arena with 16 KB guard bands on both sides, and the bands must be untouched afterwards.  (A 2-row image once wrote the next pair's
+    row 0 through exactly this kind of slip.)"""
+    from e2e_slam_b200 import ops
+    from e2e_slam_b200.synthetic import make_pairs
+    d = {k: v.cuda() for k, v in make_pairs(B, H, W, "tum", seed=W, rot_deg=6.0, trans=0.3).items()}
+    src, tgt = d["colors"][:, 0].permute(0, 3, 1, 2), d["colors"][:, 1].permute(0, 3, 1, 2)
+    plan = ops.WarpPhotoPlan(B, H, W, "cuda")
+    G = 4096                                                     # guard band, in floats
+    sizes = {"loss": 1, "grad_depth": B * H * W, "grad_src": B * 3 * H * W, "grad_P": B * 12, "vg_ws": (plan.vg_ws_bytes + 3) // 4}
+    total = sum(G + ((n + 63) // 64) * 64 for n in sizes.values()) + G
+    arena = torch.full((total,), -7.25, device="cuda")
+    off, views = G, {}
+    for k, n in sizes.items():
+        views[k] = arena[off:off + n]
+        off += ((n + 63) // 64) * 64 + G
+    plan.loss, plan.grad_depth = views["loss"], views["grad_depth"].view(B, 1, H, W)
+    plan.grad_src, plan.grad_P = views["grad_src"].view(B, 3, H, W), views["grad_P"].view(B, 3, 4)
+    plan._gs_strides = ops.strides4(plan.grad_src)
+    plan.vg_ws = views["vg_ws"].view(torch.uint8)[:plan.vg_ws_bytes]
+    ref = ops.WarpPhotoPlan(B, H, W, "cuda")
+    l0, gd0, gs0, gp0 = [t.clone() for t in ref.value_and_grad(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)]
+    l1, gd1, gs1, gp1 = plan.value_and_grad(d["depth"], d["inv_K"], d["K"], d["T"], src, tgt)
+    torch.cuda.synchronize()
+    assert float(l0) == float(l1) and torch.equal(gd0, gd1) and torch.equal(gp0, gp1)
+    mask = torch.ones(total, dtype=torch.bool, device="cuda")
+    off = G
+    for k, n in sizes.items():
+        mask[off:off + n] = False
+        off += ((n + 63) // 64) * 64 + G
+    assert bool((arena[mask] == -7.25).all()), "a guard band was written"
+
+
+@pytest.mark.parametrize("B,S,H,W,pad", [(2, 2, 48, 64, "border"), (1, 3, 37, 52, "zeros"), (2, 2, 270, 480, "border")])
+def test_multi_source_single_launch_equals_per_frame_sweeps(B, S, H, W, pad):
+    """e2e_warp_photo_vg_multi (S source frames per target in one launch): the loss must equal the mean of the S per-frame
+    losses (each bit-exact against the oracles elsewhere) and every gradient the sum / slice of the per-frame gradients."""
+    import e2e_slam_b200 as e2e
+    from e2e_slam_b200 import ops
+    from e2e_slam_b200.synthetic import make_pairs
+    ds = [make_pairs(B, H, W, "icl", seed=40 + s, rot_deg=3.0, trans=0.1) for s in range(S)]
+    cu = {k: v.cuda() for k, v in ds[0].items()}
+    tgt = cu["colors"][:, 1].permute(0, 3, 1, 2)
+    srcs_cl = torch.stack([d["colors"][:, 0] for d in ds], 1).cuda()                       # (B,S,H,W,3) channels-last, like the loader
+    Ts = torch.stack([d["T"] for d in ds], 1).cuda()
+    depth_a = cu["depth"].clone().requires_grad_(True)
+    src_a, T_a = srcs_cl.clone().requires_grad_(True), Ts.clone().requires_grad_(True)
+    la = ops.warp_photometric_loss_multi(depth_a, cu["inv_K"], cu["K"], T_a, src_a.permute(0, 1, 4, 2, 3), tgt, pad, True)
+    la.backward()
+    depth_b = cu["depth"].clone().requires_grad_(True)
+    src_b, T_b = srcs_cl.clone().requires_grad_(True), Ts.clone().requires_grad_(True)
+    lb = sum(e2e.warp_photometric_loss(depth_b, cu["inv_K"], cu["K"], T_b[:, s], src_b[:, s].permute(0, 3, 1, 2), tgt, pad, True)
+             for s in range(S)) / S
+    lb.backward()
+    assert abs(float(la) - float(lb)) <= 1e-6 * float(lb), (float(la), float(lb))
+    # same kernel arithmetic; the paths differ in the constant factor (1/(B S H W) vs 1/(B H W) then /S) and the atomics' order
+    assert rel_max(depth_a.grad.cpu().numpy(), depth_b.grad.cpu().numpy()) <= 1e-5
+    assert rel_max(src_a.grad.cpu().numpy(), src_b.grad.cpu().numpy()) <= 1e-5
+    assert rel_max(T_a.grad.cpu().numpy(), T_b.grad.cpu().numpy()) <= 5e-5

@@ -12,3 +12,4 @@ from benchmarks import fusion_bench  # noqa: E402
 r = fusion_bench.run(torch.device("cuda", 0), repeats=5)
 print(json.dumps({k: r[k] for k in ("value", "ms_per_sequence", "final_map_points", "gpu_launches")} | {"frac": r["roofline"]["frac"],
                   "mode": os.environ.get("E2E_FUSION_SEQUENCE", "coop")}))
+print(json.dumps(r.get("batched")))
