@@ -290,7 +290,7 @@ def run_ours(args):
         from e2e_slam_b200.distributed import FlatGradBucket
         stand_in = torch.nn.Parameter(torch.zeros(GRAD_BUCKET_ELEMS, device=dev))
         stand_in.grad = torch.full_like(stand_in, float(rank))
-        bucket = FlatGradBucket([stand_in], device=dev).adopt_grads()     # .grad is a view into the bucket: the step moves no extra bytes
+        bucket = FlatGradBucket([stand_in], device=dev, nvls=not args.no_nvls, nvls_ctas=args.nvls_ctas).adopt_grads()   # .grad = a view into the bucket
 
     def make_shard(mode):
         """This rank's pairs, resident in HBM.  strong: rank r owns pairs r::G of the global 256; weak: 256 pairs of its own."""
@@ -476,7 +476,7 @@ def run_ours(args):
     # ---- the same end-to-end step with the frames crossing PCIe as 8-bit images (what the datasets hold): reported next to
     # `e2e`, not instead of it -- the reference's own pipeline uploads fp32 frames (train_depth.py:255-261) ----------------
     e2e_u8 = None
-    if world == 1:
+    if True:
         host_u8 = {k: v for k, v in host.items() if k != "colors"}
         col_u8 = (d["colors"] * 255.0).round().clamp(0, 255).to(torch.uint8)
         host_u8["colors_u8"] = torch.empty(col_u8.shape, dtype=torch.uint8, pin_memory=True).copy_(col_u8)
@@ -511,7 +511,11 @@ def run_ours(args):
             l8 = e2e_u8_step()
         sync_all()
         dt8 = time.perf_counter() - t0
-        e2e_u8 = {"value": px_per_step * e2e_steps / dt8, "unit": "px/s", "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": 4,
+        if world > 1:
+            t = torch.tensor([dt8], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt8 = float(t)
+        e2e_u8 = {"value": px_per_step * e2e_steps / dt8, "unit": "px/s", "h2d_bytes_per_step": h2d_u8 * world, "d2h_bytes_per_step": 4 * world,
                   "loss": l8, "note": "frames uploaded as uint8 and divided by 255 on the device (bit-identical to the host division); "
                                       "depth, K, T as fp32"}
         del host_u8
@@ -593,6 +597,30 @@ def run_ours(args):
                "brute_force_pairs_avoided": float(P1n) * P2n, "kernel": "uniform-grid exact kNN (bit-identical to brute force)"}
         del ref, qry, uv
 
+    # ---- secondary: config C5 scale 0 -- 1080x1920, S = 2 source frames per target, ONE multi-source launch (108 B/px per target px) ----
+    c5 = None
+    if world == 1:
+        try:
+            Bc, Hc, Wc, Sc = 16, 1080, 1920, 2
+            ds5 = [make_pairs(Bc, Hc, Wc, "icl", seed=70 + s_, device=dev) for s_ in range(Sc)]
+            tgt5 = ds5[0]["colors"][:, 1].permute(0, 3, 1, 2)
+            src5 = torch.stack([x["colors"][:, 0] for x in ds5], 1)
+            T5 = torch.stack([x["T"] for x in ds5], 1)
+
+            def c5_step():
+                d_ = ds5[0]["depth"].detach().requires_grad_(True)
+                s_ = src5.detach().requires_grad_(True)
+                ops.warp_photometric_loss_multi(d_, ds5[0]["inv_K"], ds5[0]["K"], T5, s_.permute(0, 1, 4, 2, 3), tgt5).backward()
+            rewarm()
+            c5_ms, _, _ = timed_median(c5_step, n=10, warm=3)
+            c5 = {"workload": "C5 scale 0: 16 targets 1080x1920, S = 2 source frames each, loss + gradients (depth, sources) through autograd, one sweep launch",
+                  "ms": c5_ms, "warped_px_per_s": Bc * Sc * Hc * Wc / (c5_ms * 1e-3), "algorithmic_bytes_per_target_px": 36 + 36 * Sc,
+                  "frac_of_hbm_peak": (36 + 36 * Sc) * Bc * Hc * Wc / (c5_ms * 1e-3) / 1e9 / peak, "includes": "grad_src zero-fill (0.8 GB) and autograd overhead"}
+            del ds5, tgt5, src5, T5
+            torch.cuda.empty_cache()
+        except Exception as e:
+            c5 = {"error": str(e)[:200]}
+
     # ---- secondary: config C2 refinement step (single TUM pair, full loss mix), latency eager / CUDA graph --------
     c2 = None
     if world == 1 and not args.skip_fusion:
@@ -640,7 +668,9 @@ def run_ours(args):
                 "l2_policy": "inputs (2.2 GB per 256 pairs) larger than L2; no explicit flush" if P * 8.6e6 > 200e6 else
                              "inputs of one step exceed L2 (126 MB); no explicit flush",
                 "zero_fill": "grad_src is cleared every step; the buffer for the next step is cleared on a side stream during this step's kernel",
-                "collective": None if world == 1 else f"NCCL all-reduce of {GRAD_BUCKET_ELEMS} fp32 depth-net gradients per step, overlapped"
+                "collective": None if world == 1 else (f"all-reduce(mean) of {GRAD_BUCKET_ELEMS} fp32 depth-net gradients per step, overlapped; " +
+                                                       ("own NVLS kernel (multimem.ld_reduce / multimem.st over symmetric memory)" if bucket.uses_nvls
+                                                        else f"NCCL (NVLS kernel unavailable: {bucket.nvls_error})" if not args.no_nvls else "NCCL"))
                                                        + (f", NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}" if os.environ.get("NCCL_MAX_CTAS") else ""),
                 "cores_per_rank": cores_per_rank})
     out = {
@@ -655,7 +685,7 @@ def run_ours(args):
         "roofline": roof, "two_kernel_path": roof_two,
         ("weak_scaling" if scaling == "strong" else "strong_scaling"): other,
         "cpu_baseline": cpu, "torch_cuda_baseline": tc, "fusion": fusion, "single_pair": single, "c2_refinement_step": c2,
-        "point_supervision": knn, "loss": main_loss,
+        "point_supervision": knn, "c5_multi_source": c5, "loss": main_loss,
     }
     print(json.dumps(out))
     if world > 1:
@@ -675,6 +705,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=256)
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--nccl-max-ctas", type=int, default=0)
+    ap.add_argument("--no-nvls", action="store_true", help="N > 1: all-reduce the gradient bucket with NCCL instead of the NVLS multimem kernel")
+    ap.add_argument("--nvls-ctas", type=int, default=0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-fusion", action="store_true")
     ap.add_argument("--skip-torch-cuda", action="store_true")

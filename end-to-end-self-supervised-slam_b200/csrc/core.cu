@@ -108,10 +108,11 @@ __global__ void __launch_bounds__(256) u8_to_unit_kernel(const uchar4 *in, long 
                              __fdiv_rn((float)v.w, 255.0f));
     }
 }
-__global__ void u8_to_unit_tail_kernel(const unsigned char *in, long long from, long long n, float *out)
+// scalar form: the tail of an aligned array, or the whole of a misaligned one (a contiguous uint8 VIEW may start at any byte)
+__global__ void __launch_bounds__(256) u8_to_unit_scalar_kernel(const unsigned char *in, long long from, long long n, float *out)
 {
-    const long long i = from + threadIdx.x;
-    if (i < n) out[i] = __fdiv_rn((float)in[i], 255.0f);
+    for (long long i = from + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        out[i] = __fdiv_rn((float)in[i], 255.0f);
 }
 
 }  // namespace e2e
@@ -121,9 +122,9 @@ extern "C" {
 int e2e_u8_to_unit(const unsigned char *in, long long n, float *out, void *stream)
 {
     E2E_REQUIRE(in && out && n > 0, "u8_to_unit: bad arguments");
-    E2E_REQUIRE((((uintptr_t)in) & 3) == 0 && (((uintptr_t)out) & 15) == 0, "u8_to_unit: input must be 4-byte, output 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long n4 = n / 4;
+    const bool vec = (((uintptr_t)in) & 3) == 0 && (((uintptr_t)out) & 15) == 0;
+    const long long n4 = vec ? n / 4 : 0;
     if (n4 > 0) {
         long long blocks = (n4 + 255) / 256;
         if (blocks > e2e::kNumSMs * 16) blocks = e2e::kNumSMs * 16;
@@ -131,7 +132,9 @@ int e2e_u8_to_unit(const unsigned char *in, long long n, float *out, void *strea
         e2e::count_launch();
     }
     if (n4 * 4 < n) {
-        e2e::u8_to_unit_tail_kernel<<<1, 4, 0, st>>>(in, n4 * 4, n, out);
+        long long blocks = (n - n4 * 4 + 255) / 256;
+        if (blocks > e2e::kNumSMs * 16) blocks = e2e::kNumSMs * 16;
+        e2e::u8_to_unit_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, n4 * 4, n, out);
         e2e::count_launch();
     }
     return e2e::finish_launch("u8_to_unit");

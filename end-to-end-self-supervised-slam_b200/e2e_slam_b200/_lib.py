@@ -81,6 +81,7 @@ _SIGNATURES = {
     "e2e_fusion_sequence_batch_workspace_bytes": (_SZ, [_I, _I, _I, _LL]),
     "e2e_fusion_sequence_batch": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _LL, _P, _SZ, _P]),
     "e2e_fusion_merge_append_bwd": (_I, [_P] * 11 + [_I, _I] + [_P] * 7),
+    "e2e_multimem_allreduce_avg": (_I, [_P, _LL, _I, _I, _I, _P]),
     "e2e_knn1_fwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P]),
     "e2e_knn1_bwd": (_I, [_P, _P, _P, _LL, _LL, _P, _P, _P, _P, _P]),
     "e2e_transform_points_fwd": (_I, [_P, _P, _LL, _P, _P]),

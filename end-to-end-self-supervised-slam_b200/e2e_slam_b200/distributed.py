@@ -9,7 +9,16 @@ main stream does next.  PointFusion over one sequence does not shard (frame s fu
 s-1): replicas only, one sequence per rank.
 
 One process per GPU (torchrun); backend "nccl" on GPUs, "gloo" in the CPU tests.
+
+On an NVSwitch box the bucket's all-reduce is OUR kernel (csrc/multimem_allreduce.cu, `FlatGradBucket(..., nvls=True)`): the bucket
+is allocated in symmetric memory, rank r reduces slice r inside the switch with `multimem.ld_reduce` and broadcasts the mean with
+`multimem.st`, bracketed by two cross-rank barriers -- a few CTAs for the time the switch needs, instead of NCCL's ring kernel holding
+16-32 SMs next to an issue-bound sweep.  torch.distributed._symmetric_memory provides allocation, rendezvous and the barrier
+(plumbing); without multicast support the bucket falls back to the NCCL all-reduce.
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -31,16 +40,43 @@ class FlatGradBucket:
     grad is None on some rank contributes zeros.  Frozen parameters (refinement mode freezes every tensor
     whose name contains "bn", train_depth.py:213-222) are not members."""
 
-    def __init__(self, params, process_group=None, device=None):
+    def __init__(self, params, process_group=None, device=None, nvls=False, nvls_ctas=0):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         self.group = process_group
         self.device = torch.device(device) if device is not None else self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self._work = None
+        self._symm, self.nvls_ctas, self.nvls_error = None, int(nvls_ctas), None
+        self.flat = None
+        if nvls and self.device.type == "cuda" and os.environ.get("E2E_NVLS", "1") != "0":
+            self._try_nvls()
+        if self.flat is None:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+
+    def _try_nvls(self):
+        """Bucket in symmetric memory with a multicast mapping; any failure (no NVSwitch, no multicast support, an older torch)
+        leaves the NCCL path in place and records why."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            padded = (self.numel + 3) // 4 * 4
+            buf = symm_mem.empty(padded, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(buf, group)
+            if not int(getattr(hdl, "multicast_ptr", 0)):
+                raise RuntimeError("the symmetric-memory handle has no multicast address (no NVLS on this system)")
+            buf.zero_()
+            self._symm, self._symm_buf, self._padded = hdl, buf, padded
+            self.flat = buf[:self.numel]
+        except Exception as e:                        # noqa: BLE001 -- every reason means "use NCCL"
+            self._symm, self.flat = None, None
+            self.nvls_error = f"{type(e).__name__}: {e}"[:300]
+
+    @property
+    def uses_nvls(self):
+        return self._symm is not None
 
     def _views(self):
         off = 0
@@ -80,7 +116,16 @@ class FlatGradBucket:
                     v.zero_()
                 else:
                     v.copy_(p.grad)
-            if self.device.type == "cuda":
+            if self._symm is not None:
+                from ._lib import check, lib
+                hdl = self._symm
+                hdl.barrier(channel=0)                  # every rank's gradients are in its copy of the bucket
+                check(lib().e2e_multimem_allreduce_avg(ctypes.c_void_p(int(hdl.multicast_ptr)), self._padded, hdl.rank, hdl.world_size,
+                                                       self.nvls_ctas, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                      "e2e_multimem_allreduce_avg")
+                hdl.barrier(channel=1)                  # every slice is reduced and written back everywhere
+                self._work = True
+            elif self.device.type == "cuda":
                 self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             else:
                 self.flat.div_(world)
@@ -91,7 +136,8 @@ class FlatGradBucket:
         """Wait for the all-reduce and hand the averaged gradients back (no copy for gradients that are bucket views)."""
         if self._work is None:
             raise RuntimeError("finish() called before start()")
-        self._work.wait()
+        if self._work is not True:
+            self._work.wait()
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         for p, v in self._views():

@@ -156,6 +156,9 @@ def depth_reguralizer(initial_depth, refined_depth, loss_func):
     f32(initial_depth, "initial_depth"), f32(refined_depth, "refined_depth")
     if initial_depth.shape != refined_depth.shape:
         raise ValueError("initial and refined depth must have the same shape")
+    if torch.is_grad_enabled() and initial_depth.requires_grad:
+        raise NotImplementedError("depth_reguralizer differentiates refined_depth only (the reference passes a detached clone as "
+                                  "initial_depth, train_depth.py:336); detach it or swap the arguments")
     return _EwLoss.apply(loss_func, initial_depth.detach().contiguous(), refined_depth.contiguous(), None)
 
 

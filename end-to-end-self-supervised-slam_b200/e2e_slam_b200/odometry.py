@@ -28,13 +28,18 @@ def se3_exp(xi):
     K = torch.stack([torch.stack([z, -w[2], w[1]]), torch.stack([w[2], z, -w[0]]), torch.stack([-w[1], w[0], z])])
     t2 = (w * w).sum()
     eye = torch.eye(3, dtype=xi.dtype, device=xi.device)
-    if float(t2.detach()) < 1e-12:
-        R, V = eye + K, eye + 0.5 * K
-    else:
-        t = torch.sqrt(t2)
-        K2 = K @ K
-        R = eye + torch.sin(t) / t * K + (1 - torch.cos(t)) / t2 * K2
-        V = eye + (1 - torch.cos(t)) / t2 * K + (t - torch.sin(t)) / (t2 * t) * K2
+    # branch-free (no host read of t2: this runs every iteration of the autograd ICP route): below t^2 = 1e-12 the first-order
+    # forms R = I + K, V = I + K / 2; the large-angle coefficients are evaluated on a safe argument there
+    small = t2 < 1e-12
+    one = torch.ones((), dtype=xi.dtype, device=xi.device)
+    t2s = torch.where(small, one, t2)
+    t = torch.sqrt(t2s)
+    K2 = K @ K
+    a = torch.where(small, one, torch.sin(t) / t)
+    b = (1 - torch.cos(t)) / t2s
+    c = torch.where(small, torch.zeros_like(one), (t - torch.sin(t)) / (t2s * t))
+    R = eye + a * K + torch.where(small, torch.zeros_like(one), b) * K2
+    V = eye + torch.where(small, 0.5 * one, b) * K + c * K2
     top = torch.cat([R, (V @ v).unsqueeze(1)], 1)
     bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=xi.dtype, device=xi.device)
     return torch.cat([top, bottom], 0)
@@ -86,7 +91,7 @@ def _library_icp(src_pc, tgt_pc, tgt_normals, initial_transform, numiters, damp,
     dev = src.device
     N, M = src.shape[0], tgt.shape[0]
     T_out = torch.empty(4, 4, dtype=torch.float32, device=dev)
-    idx = torch.empty(N, dtype=torch.int64, device=dev)
+    idx = torch.zeros(N, dtype=torch.int64, device=dev) if int(numiters) <= 0 else torch.empty(N, dtype=torch.int64, device=dev)
     nws = lib().e2e_icp_workspace_bytes(N, M)
     ws = torch.empty(nws, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

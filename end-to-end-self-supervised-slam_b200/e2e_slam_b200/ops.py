@@ -63,6 +63,9 @@ class _WarpPhotometric(torch.autograd.Function):
         B, _, H, W = depth.shape
         if tuple(src.shape) != (B, 3, H, W) or tuple(tgt.shape) != (B, 3, H, W):
             raise ValueError(f"source/target frames must be ({B},3,{H},{W}), got {tuple(src.shape)} / {tuple(tgt.shape)}")
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("the fused op does not differentiate inv_K (the reference derives it from the dataset's K with "
+                                      "torch.pinverse outside the graph, train_depth.py:460-461); detach it")
         depth_c = depth.contiguous()
         inv_K_c, K_c, T_c = _mat44(inv_K, B, "inv_K"), _mat44(K, B, "K"), _mat44(T, B, "T")
         prepare_divisors(W - 1, H - 1, 9.0, 3.0)
@@ -194,6 +197,9 @@ class _WarpPhotometricMean(torch.autograd.Function):
         B, _, H, W = depth.shape
         if tuple(src.shape) != (B, 3, H, W) or tuple(tgt.shape) != (B, 3, H, W):
             raise ValueError(f"source/target frames must be ({B},3,{H},{W}), got {tuple(src.shape)} / {tuple(tgt.shape)}")
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("the fused op does not differentiate inv_K (the reference derives it from the dataset's K with "
+                                      "torch.pinverse outside the graph, train_depth.py:460-461); detach it")
         depth_c = depth.contiguous()
         inv_K_c, K_c, T_c = _mat44(inv_K, B, "inv_K"), _mat44(K, B, "K"), _mat44(T, B, "T")
         prepare_divisors(W - 1, H - 1, 9.0, 3.0)

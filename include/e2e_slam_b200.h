@@ -405,6 +405,14 @@ int e2e_disp_to_depth_bwd(const float *disp, const float *ratio, const float *gr
 int e2e_dual_disparity_fwd(const float *left, const float *right, const float *row_mask, int H, int W, float *out, void *stream);
 int e2e_dual_disparity_bwd(const float *grad_out, const float *row_mask, int H, int W, float *grad_left, float *grad_right, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: the one collective of the data-parallel path -- all-reduce(mean) of the depth network's adaptation
+ * gradients (~57 MB fp32) -- as an NVLS kernel: `multicast_ptr` is the multicast address of a symmetric-memory bucket of `numel`
+ * floats (multiple of 4, 16-byte aligned); rank r reduces the r-th slice in the switch (multimem.ld_reduce) and broadcasts the mean
+ * (multimem.st).  The caller brackets the call with cross-rank barriers on the same stream.  `ctas` <= 0: default (8).
+ * --------------------------------------------------------------------------------------------- */
+int e2e_multimem_allreduce_avg(void *multicast_ptr, long long numel, int rank, int world, int ctas, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,3 +91,11 @@ def test_flat_bucket_allreduce_world2():
         p.join(120)
         assert p.exitcode == 0
     assert out.get() is True
+
+
+def test_bucket_without_nvls_support_falls_back():
+    """nvls=True on a device without NVLS (here: the CPU) must leave the ordinary bucket in place, not fail."""
+    from e2e_slam_b200.distributed import FlatGradBucket
+    p = torch.nn.Parameter(torch.zeros(10))
+    b = FlatGradBucket([p], device="cpu", nvls=True)
+    assert not b.uses_nvls and b.flat.shape == (10,) and b.flat.device.type == "cpu"
