@@ -25,6 +25,15 @@ namespace e2e {
 constexpr int KG_NT = 256;
 constexpr int KG_MAX_CELLS = 1 << 24;
 constexpr int KG_PASSES = 4;
+#ifndef KG_M_VAL
+#define KG_M_VAL 4
+#endif
+constexpr int KG_M = KG_M_VAL;               // fine cells per coarse cell and axis
+constexpr int KG_M3 = KG_M * KG_M * KG_M;
+// Cell numbering: COARSE-MAJOR.  A fine cell (x, y, z) has the id  coarse(x/M, y/M, z/M) * M^3 + ((z%M) * M + y%M) * M + x%M,  so the
+// points of one coarse cell are ONE contiguous range of the sorted records (start[cc * M^3] .. start[(cc + 1) * M^3]) and the far
+// search walks it as a flat list, 32 points per warp step.  The occupancy bitmap keeps the LINEAR numbering ((z * ny + y) * nx + x):
+// the near search fetches an x-row of occupancy bits with one funnel shift.  ncells counts the padded (coarse-major) ids.
 
 struct GridParams {
     float ox, oy, oz;      // origin (bbox minimum)
@@ -90,14 +99,14 @@ __device__ void kg_set_cells(GridParams *gp, float h)
         double cells = 1.0;
         for (int k = 0; k < 3; k++) {
             n[k] = (int)fmin(floor((double)gp->ext[k] / (double)h) + 1.0, 2097152.0);
-            cells *= (double)n[k];
+            cells *= (double)((n[k] + KG_M - 1) / KG_M * KG_M);      // ids are padded to whole coarse cells per axis
         }
         if (cells <= (double)KG_MAX_CELLS) break;
         h *= 1.26f;
     }
     gp->h = h; gp->inv_h = 1.0f / h;
     gp->nx = n[0]; gp->ny = n[1]; gp->nz = n[2];
-    gp->ncells = n[0] * n[1] * n[2];
+    gp->ncells = ((n[0] + KG_M - 1) / KG_M) * ((n[1] + KG_M - 1) / KG_M) * ((n[2] + KG_M - 1) / KG_M) * KG_M3;
 }
 
 __global__ void kg_params_kernel(const unsigned *bb, long long P2, GridParams *gp)
@@ -153,13 +162,20 @@ __device__ __forceinline__ int cell_coord(float v, float o, float inv_h)
     return (int)c;
 }
 
+// coarse-major id of the fine cell (x, y, z) (inside the grid)
+__device__ __forceinline__ int cell_id(const GridParams &g, int x, int y, int z)
+{
+    const int mx = (g.nx + KG_M - 1) / KG_M, my = (g.ny + KG_M - 1) / KG_M;
+    return (((z / KG_M) * my + y / KG_M) * mx + x / KG_M) * KG_M3 + ((z % KG_M) * KG_M + y % KG_M) * KG_M + x % KG_M;
+}
+
 __device__ __forceinline__ int ref_cell(const GridParams &g, float x, float y, float z)
 {
     if (!(isfinite(x) && isfinite(y) && isfinite(z))) return 0;     // never the nearest of anything: where it sits is irrelevant
     const int cx = min(max(cell_coord(x, g.ox, g.inv_h), 0), g.nx - 1);
     const int cy = min(max(cell_coord(y, g.oy, g.inv_h), 0), g.ny - 1);
     const int cz = min(max(cell_coord(z, g.oz, g.inv_h), 0), g.nz - 1);
-    return (cz * g.ny + cy) * g.nx + cx;
+    return cell_id(g, cx, cy, cz);
 }
 
 __global__ void __launch_bounds__(KG_NT) kg_count_kernel(const float *ref, long long P2, GridParams *gp, int *cell_of, int *count)
@@ -268,13 +284,16 @@ __global__ void __launch_bounds__(KG_NT) kg_fill_kernel(const float *ref, long l
     }
 }
 
-#ifndef KG_M_VAL
-#define KG_M_VAL 4
-#endif
-constexpr int KG_M = KG_M_VAL;               // fine cells per coarse cell and axis (coarse cells only record whether anything is inside)
 // measured (307 200 queries ~7 cm off a 2 M-point surface / config C2 step): M = 2: 2.57 / 4.67 ms, 3: 1.85 / 2.56, 4: 1.63 / 1.95,
 // 6: 1.82 / 2.30, 8: 1.95 / 2.56 -- smaller cells lengthen the ring walk, larger ones loosen the boxes and the search per cell
-constexpr int KG_NEAR_RINGS = 2;      // rings of fine cells searched directly around the query
+#ifndef KG_NEAR_RINGS_VAL
+#define KG_NEAR_RINGS_VAL 1
+#endif
+// rings of fine cells searched directly around the query (one thread per query).  Measured with the flat-list far search (build +
+// query, 307 200 queries vs 2 M points, mean distance 0 / 2 / 7 / 15 cm; 19 200 x 75 000): 2 rings 0.44 / 0.76 / 1.13 / 1.98 / 0.26 ms,
+// 1 ring 0.45 / 0.54 / 0.92 / 1.81 / 0.19 ms -- a second ring walked by single threads is mostly futile work for queries that go
+// to the warp-per-query search anyway
+constexpr int KG_NEAR_RINGS = KG_NEAR_RINGS_VAL;
 #ifndef KG_FAR_MINB
 #define KG_FAR_MINB 6      // latency bound: 48 warps per SM (40 registers, a few outer-loop values spilled) measured faster than 32 or 24
 #endif
@@ -286,9 +305,12 @@ __global__ void __launch_bounds__(KG_NT) kg_coarse_kernel(long long P2, const Gr
     const GridParams g = *gp;
     const int mx = (g.nx + KG_M - 1) / KG_M, my = (g.ny + KG_M - 1) / KG_M;
     for (long long i = (long long)blockIdx.x * KG_NT + threadIdx.x; i < P2; i += (long long)gridDim.x * KG_NT) {
-        const int c = cell_of[i];
-        const int x = c % g.nx, y = (c / g.nx) % g.ny, z = c / (g.nx * g.ny);
-        atomicAdd(coarse + ((z / KG_M) * my + y / KG_M) * mx + x / KG_M, 1);
+        const int id = cell_of[i];                                   // coarse-major id -> coarse cell, linear fine cell
+        const int cc = id / KG_M3, f = id % KG_M3;
+        const int X = cc % mx, Y = (cc / mx) % my, Z = cc / (mx * my);
+        const int x = X * KG_M + f % KG_M, y = Y * KG_M + (f / KG_M) % KG_M, z = Z * KG_M + f / (KG_M * KG_M);
+        const int c = (z * g.ny + y) * g.nx + x;
+        atomicAdd(coarse + cc, 1);
         atomicOr(bits + (c >> 5), 1u << (c & 31));
     }
 }
@@ -299,27 +321,22 @@ __global__ void __launch_bounds__(KG_NT) kg_coarse_kernel(long long P2, const Gr
 // the nearest cell unsearched.  Floating-point subtraction is monotone, so |q - p| >= the box distance holds per axis in
 // fp32 exactly; non-finite points (never anyone's nearest) are left out.
 __global__ void __launch_bounds__(KG_NT) kg_coarse_box_kernel(const GridParams *gp, const int *start, const float4 *sorted, const int *coarse,
-                                                              const unsigned *bits, float4 *cbox)
+                                                              float4 *cbox)
 {
     const GridParams g = *gp;
     const int lane = threadIdx.x & 31;
-    const int mx = (g.nx + KG_M - 1) / KG_M, my = (g.ny + KG_M - 1) / KG_M, mz = (g.nz + KG_M - 1) / KG_M;
-    const long long total = (long long)mx * my * mz;
+    const long long total = g.ncells / KG_M3;
     for (long long cc = (long long)blockIdx.x * (KG_NT / 32) + (threadIdx.x >> 5); cc < total; cc += (long long)gridDim.x * (KG_NT / 32)) {
-        if (coarse[cc] == 0) continue;
-        const int cX = (int)(cc % mx), cY = (int)((cc / mx) % my), cZ = (int)(cc / ((long long)mx * my));
+        if (coarse[cc] == 0) {      // empty: an empty range (the far search reads box and range of every candidate cell, never `coarse`)
+            if (lane == 0) cbox[2 * cc] = cbox[2 * cc + 1] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+            continue;
+        }
         float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
-        for (int f = lane; f < KG_M * KG_M * KG_M; f += 32) {
-            const int x = cX * KG_M + (f % KG_M), y = cY * KG_M + (f / KG_M) % KG_M, z = cZ * KG_M + f / (KG_M * KG_M);
-            if (x >= g.nx || y >= g.ny || z >= g.nz) continue;
-            const int c = (z * g.ny + y) * g.nx + x;
-            if (!((bits[c >> 5] >> (c & 31)) & 1u)) continue;
-            for (int j = start[c], e = start[c + 1]; j < e; j++) {
-                const float4 p = sorted[j];
-                if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-                    lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
-                    hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
-                }
+        for (int j = start[cc * KG_M3] + lane, e = start[(cc + 1) * KG_M3]; j < e; j += 32) {      // the cell's points: one contiguous range
+            const float4 p = sorted[j];
+            if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+                lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
+                hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
             }
         }
 #pragma unroll
@@ -329,8 +346,9 @@ __global__ void __launch_bounds__(KG_NT) kg_coarse_box_kernel(const GridParams *
             hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
         }
         if (lane == 0) {
-            cbox[2 * cc] = make_float4(lx, ly, lz, 0.0f);
-            cbox[2 * cc + 1] = make_float4(hx, hy, hz, 0.0f);
+            // the w slots carry the cell's range of sorted records, so that the far search gets box and range with the same two loads
+            cbox[2 * cc] = make_float4(lx, ly, lz, __int_as_float(start[cc * KG_M3]));
+            cbox[2 * cc + 1] = make_float4(hx, hy, hz, __int_as_float(start[(cc + 1) * KG_M3]));
         }
     }
 }
@@ -386,8 +404,10 @@ __global__ void __launch_bounds__(KG_NT) kg_query_near_kernel(const float *query
                         const int c0 = (z * g.ny + y) * g.nx + xlo;
                         unsigned m = __funnelshift_r(bits[c0 >> 5], bits[(c0 >> 5) + 1], c0 & 31) & xmask;
                         if (abs(dz) < R && abs(dy) < R) m &= ~inner;
+                        const int rowid = cell_id(g, 0, y, z);                  // coarse-major id of the row's cell x = 0
                         while (m) {
-                            const int c = c0 + __ffs(m) - 1;
+                            const int x = xlo + __ffs(m) - 1;
+                            const int c = rowid + (x / KG_M) * KG_M3 + x % KG_M;
                             m &= m - 1;
                             for (int j = start[c], e = start[c + 1]; j < e; j++) {
                                 const float4 p = sorted[j];
@@ -421,12 +441,13 @@ __global__ void __launch_bounds__(KG_NT) kg_query_near_kernel(const float *query
 
 // Query, phase 2 -- one WARP per far query.  A thread-per-query walk of the rings diverges completely (every lane in its own
 // loop nest: measured 17 ms for 240 k queries 9 cm off a 2 M-point surface, ~45 k instructions each).  Here the warp walks
-// rings of COARSE cells around its query together: empty coarse cells are skipped, the KG_M^3 fine cells of an occupied one
-// are dealt out to the lanes, a lane skips a fine cell that is empty or farther than the best known to it, and the lanes'
-// results are merged (minimum of (distance, index)) after every coarse cell that was searched.  The search stops when the
-// best distance lies inside the fully searched cube, so the result is the brute-force result.
+// rings of COARSE cells around its query together: empty coarse cells are skipped, the points of an occupied one -- ONE
+// contiguous range of the sorted records, because cell ids are coarse-major -- are dealt out to the lanes as a flat list (round 1
+// dealt out the KG_M^3 fine cells, two per lane, each lane in its own point loop: 17 of 32 lanes active, ~50 warp iterations per
+// query), and the lanes' results are merged (minimum of (distance, index)) after every coarse cell that was searched.  The search
+// stops when the best distance lies inside the fully searched cube, so the result is the brute-force result.
 __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const float *query, const float *T, const GridParams *gp, const int *start,
-                                                             const float4 *sorted, const int *coarse, const float4 *cbox, const unsigned *bits,
+                                                             const float4 *sorted, const float4 *cbox,
                                                              float *dist2, long long *idx, const int *far_list, const int *far_count)
 {
     const GridParams g = *gp;
@@ -452,7 +473,7 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
         const int mx = (g.nx + KG_M - 1) / KG_M, my = (g.ny + KG_M - 1) / KG_M, mz = (g.nz + KG_M - 1) / KG_M;
         auto cdiv = [](int c) { return c >= 0 ? c / KG_M : -((-c + KG_M - 1) / KG_M); };      // floor division
         const int qX = cdiv(cx), qY = cdiv(cy), qZ = cdiv(cz);
-        const float hc = g.h * (float)KG_M, half = g.h * (0.5f + slack);
+        const float hc = g.h * (float)KG_M;
         // rings before the first one that can touch the grid hold nothing
         // (and the walk starts with the 27 cells of box(1) as ONE batch: nearest first works best on a whole neighbourhood)
         int r = max(max(max(-qX, qX - (mx - 1)), max(-qY, qY - (my - 1))), max(max(-qZ, qZ - (mz - 1)), 1));
@@ -490,7 +511,7 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
             const bool exact_rcp = total <= (1 << 20);
             for (int base = 0; base < total; base += 32) {
                 const int t = base + lane;
-                int X = 0, Y = 0, Z = 0;
+                int rs = 0, re = 0;              // this lane's candidate cell: its range of sorted records
                 unsigned key = 0xffffffffu;      // bits of the coarse cell's box distance (>= 0: ordered like the floats); all ones = nothing to search
                 if (t < total) {
                     int q1, q2;
@@ -502,15 +523,17 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
                         q2 = q1 / by;
                     }
                     const int x = t - q1 * bx, y = q1 - q2 * by;
-                    X = sx0 + x; Y = sy0 + y; Z = sz0 + q2;
+                    const int X = sx0 + x, Y = sy0 + y, Z = sz0 + q2;
                     const int cc = (Z * my + Y) * mx + X;
                     const bool seen = whole && !fresh && X >= pX0 && X <= pX1 && Y >= pY0 && Y <= pY1 && Z >= pZ0 && Z <= pZ1;
-                    if (!seen && coarse[cc] != 0) {      // distance to the tight box of the cell's points (kg_coarse_box_kernel)
-                        const float4 lo = cbox[2 * cc], hi = cbox[2 * cc + 1];
+                    const float4 lo = cbox[2 * cc], hi = cbox[2 * cc + 1];      // tight box of the cell's points + their range (kg_coarse_box_kernel)
+                    if (!seen && __float_as_int(hi.w) > __float_as_int(lo.w)) {
                         const float ex = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
                         const float ey = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
                         const float ez = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
                         key = __float_as_uint((ex * ex + ey * ey + ez * ez) * 0.9999f);
+                        rs = __float_as_int(lo.w);
+                        re = __float_as_int(hi.w);
                     }
                 }
                 // nearest occupied coarse cell of the batch first; `best` is the same in every lane here (merged after each
@@ -521,22 +544,23 @@ __global__ void __launch_bounds__(KG_NT, KG_FAR_MINB) kg_query_far_kernel(const 
                     if (mk == 0xffffffffu || __uint_as_float(mk) > best) break;
                     const int srcl = __ffs(__ballot_sync(0xffffffffu, key == mk)) - 1;
                     if (lane == srcl) key = 0xffffffffu;
-                    const int cX = __shfl_sync(0xffffffffu, X, srcl), cY = __shfl_sync(0xffffffffu, Y, srcl), cZ = __shfl_sync(0xffffffffu, Z, srcl);
-                    // the coarse cell's KG_M^3 fine cells, two per lane
-                    for (int f = lane; f < KG_M * KG_M * KG_M; f += 32) {
-                        const int x = cX * KG_M + (f % KG_M), y = cY * KG_M + (f / KG_M) % KG_M, z = cZ * KG_M + f / (KG_M * KG_M);
-                        if (x >= g.nx || y >= g.ny || z >= g.nz) continue;
-                        const int c = (z * g.ny + y) * g.nx + x;
-                        if (!((bits[c >> 5] >> (c & 31)) & 1u)) continue;
-                        const float ex = fmaxf(fabsf(qx - (g.ox + ((float)x + 0.5f) * g.h)) - half, 0.0f);
-                        const float ey = fmaxf(fabsf(qy - (g.oy + ((float)y + 0.5f) * g.h)) - half, 0.0f);
-                        const float ez = fmaxf(fabsf(qz - (g.oz + ((float)z + 0.5f) * g.h)) - half, 0.0f);
-                        if ((ex * ex + ey * ey + ez * ez) * 0.9999f > best) continue;      // farther than the best known to this lane
-                        for (int j = start[c], e = start[c + 1]; j < e; j++) {
-                            const float4 p = sorted[j];
+                    // the cell's points are one contiguous range of the sorted records (coarse-major cell ids): a flat list, 32
+                    // points per step, two steps in flight -- every lane works, nothing is looked up per fine cell
+                    const int s0 = __shfl_sync(0xffffffffu, rs, srcl), e0 = __shfl_sync(0xffffffffu, re, srcl);
+                    for (int j = s0 + lane; j < e0; j += 64) {
+                        const bool two = j + 32 < e0;
+                        const float4 p = sorted[j];
+                        const float4 p2 = sorted[two ? j + 32 : j];
+                        {
                             const float dx = xsub(qx, p.x), dy = xsub(qy, p.y), dz = xsub(qz, p.z);
                             const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
                             const int pi = __float_as_int(p.w);
+                            if (d2 <= best) { if (d2 < best || pi < bi) { best = d2; bi = pi; } }
+                        }
+                        {
+                            const float dx = xsub(qx, p2.x), dy = xsub(qy, p2.y), dz = xsub(qz, p2.z);
+                            const float d2 = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+                            const int pi = __float_as_int(p2.w);
                             if (d2 <= best) { if (d2 < best || pi < bi) { best = d2; bi = pi; } }
                         }
                     }
@@ -603,7 +627,7 @@ int e2e_knn1_grid_build(const float *ref, long long P2, void *workspace, size_t 
     int *coarse = (int *)w;             w += kg_a256(KG_COARSE * 4);
     unsigned *bits = (unsigned *)w;     w += kg_a256(KG_PADDED / 8);
     unsigned *bb = (unsigned *)w;       w += 3 * 256;      // bbox words, far-query counter
-    float4 *cbox = (float4 *)w;         // written for occupied coarse cells only, read only where coarse != 0: no clear
+    float4 *cbox = (float4 *)w;         // box + record range of every coarse cell (kg_coarse_box_kernel writes all of them: no clear)
     // bbox accumulators: minima start at all ones, maxima at zero (ordered encoding); the histogram's padding stays zero
     if (cudaMemsetAsync(bb, 0xff, 12, st) != cudaSuccess || cudaMemsetAsync(bb + 3, 0x00, 12, st) != cudaSuccess ||
         cudaMemsetAsync(start, 0, KG_PADDED * 4, st) != cudaSuccess || cudaMemsetAsync(coarse, 0, KG_COARSE * 4 , st) != cudaSuccess ||
@@ -622,7 +646,7 @@ int e2e_knn1_grid_build(const float *ref, long long P2, void *workspace, size_t 
     kg_scan3_kernel<<<chunks, 1024, 0, st>>>(start, chunk_sum, cursor, gp);
     kg_fill_kernel<<<nb, KG_NT, 0, st>>>(ref, P2, cell_of, cursor, sorted);
     kg_coarse_kernel<<<nb, KG_NT, 0, st>>>(P2, gp, cell_of, coarse, bits);
-    kg_coarse_box_kernel<<<kNumSMs * 16, KG_NT, 0, st>>>(gp, start, sorted, coarse, bits, cbox);
+    kg_coarse_box_kernel<<<kNumSMs * 16, KG_NT, 0, st>>>(gp, start, sorted, coarse, cbox);
     count_launch(2 + 3 * KG_PASSES - 1 + 6);
     return finish_launch("knn1_grid_build");
 }
@@ -649,7 +673,7 @@ int e2e_knn1_grid_query(const float *query, const float *transform, long long P1
     kg_query_near_kernel<<<(unsigned)qb, KG_NT, 0, st>>>(query, transform, P1, gp, start, sorted, bits, dist2, idx, far_list, far_count);
     long long fb = (P1 + KG_NT / 32 - 1) / (KG_NT / 32);
     if (fb > kNumSMs * 32) fb = kNumSMs * 32;
-    kg_query_far_kernel<<<(unsigned)fb, KG_NT, 0, st>>>(query, transform, gp, start, sorted, coarse, cbox, bits, dist2, idx, far_list, far_count);
+    kg_query_far_kernel<<<(unsigned)fb, KG_NT, 0, st>>>(query, transform, gp, start, sorted, cbox, dist2, idx, far_list, far_count);
     count_launch(2);
     return finish_launch("knn1_grid_query");
 }
