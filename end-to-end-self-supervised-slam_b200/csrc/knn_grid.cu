@@ -26,7 +26,7 @@ constexpr int KG_NT = 256;
 constexpr int KG_MAX_CELLS = 1 << 24;
 constexpr int KG_PASSES = 4;
 #ifndef KG_M_VAL
-#define KG_M_VAL 4
+#define KG_M_VAL 6
 #endif
 constexpr int KG_M = KG_M_VAL;               // fine cells per coarse cell and axis
 constexpr int KG_M3 = KG_M * KG_M * KG_M;
@@ -284,8 +284,10 @@ __global__ void __launch_bounds__(KG_NT) kg_fill_kernel(const float *ref, long l
     }
 }
 
-// measured (307 200 queries ~7 cm off a 2 M-point surface / config C2 step): M = 2: 2.57 / 4.67 ms, 3: 1.85 / 2.56, 4: 1.63 / 1.95,
-// 6: 1.82 / 2.30, 8: 1.95 / 2.56 -- smaller cells lengthen the ring walk, larger ones loosen the boxes and the search per cell
+// measured with the flat-list far search (build + query, 307 200 queries 7 / 15 cm off a 2 M-point surface / config C2 step as a CUDA
+// graph): M = 2: 1.94 / 3.76 / 5.79 ms, 3: 1.10 / 1.82 / 2.34, 4: 0.93 / 1.39 / 1.70, 5: 0.88 / 1.22 / 1.37, 6: 0.80 / 1.06 / 1.35,
+// 7: 0.83 / 1.07 / 1.44, 8: 0.87 / 1.08 / 1.55, 10: 0.96 / 1.16 / 1.82, 12: 1.04 / 1.26 / 2.17 -- smaller cells lengthen the ring walk,
+// larger ones lengthen the point lists.  (Round 1's per-lane fine-cell loops had their optimum at M = 4: 1.63 / - / 1.95 ms.)
 #ifndef KG_NEAR_RINGS_VAL
 #define KG_NEAR_RINGS_VAL 1
 #endif
