@@ -451,3 +451,37 @@ def test_multi_source_single_launch_equals_per_frame_sweeps(B, S, H, W, pad):
     assert rel_max(depth_a.grad.cpu().numpy(), depth_b.grad.cpu().numpy()) <= 1e-5
     assert rel_max(src_a.grad.cpu().numpy(), src_b.grad.cpu().numpy()) <= 1e-5
     assert rel_max(T_a.grad.cpu().numpy(), T_b.grad.cpu().numpy()) <= 5e-5
+
+
+@pytest.mark.parametrize("B,H,W,disp", [(2, 48, 64, False), (1, 9, 12, False), (3, 120, 160, True), (2, 480, 640, False), (1, 271, 480, False)])
+def test_role_split_kernel_equals_classic_kernel(monkeypatch, B, H, W, disp):
+    """E2E_ROLES=1 runs the lean value + gradient sweep on warp_photo_roles_kernel (three warp groups, progress mbarriers, 8-step
+    rings -- DESIGN.md section 5) instead of the classic streaming kernel: same strip walk and per-pixel arithmetic, so loss,
+    grad_depth and grad_P are bit-identical and grad_src differs only by the order of the red.global.add atomics."""
+    import e2e_slam_b200 as e2e
+    from e2e_slam_b200 import ops
+    from e2e_slam_b200.synthetic import make_pairs
+    d = make_pairs(B, H, W, "tum", seed=H + W, rot_deg=3.0, trans=0.1)
+    cu = {k: v.cuda() for k, v in d.items()}
+    src0, tgt = cu["colors"][:, 0].permute(0, 3, 1, 2), cu["colors"][:, 1].permute(0, 3, 1, 2)
+
+    def run(roles):
+        monkeypatch.setenv("E2E_ROLES", "1" if roles else "0")
+        depth = cu["depth"].clone().requires_grad_(True)
+        src = src0.clone().requires_grad_(True)
+        T = cu["T"].clone().requires_grad_(True)
+        if disp:
+            x = (1.0 / cu["depth"]).clone().requires_grad_(True)
+            loss = ops.warp_photometric_loss_from_disparity(x, cu["inv_K"], cu["K"], T, src, tgt, torch.tensor(1.1, device="cuda"), "border", True)
+            loss.backward()
+            return loss.detach(), x.grad, src.grad, T.grad
+        loss = e2e.warp_photometric_loss(depth, cu["inv_K"], cu["K"], T, src, tgt, "border", True)
+        loss.backward()
+        return loss.detach(), depth.grad, src.grad, T.grad
+
+    l0, gd0, gs0, gt0 = run(False)
+    l1, gd1, gs1, gt1 = run(True)
+    assert float(l0) == float(l1)
+    assert torch.equal(gd0, gd1)
+    assert torch.equal(gt0, gt1)
+    assert rel_max(gs1.cpu().numpy(), gs0.cpu().numpy()) <= 2e-6

@@ -1,0 +1,4 @@
+#!/bin/bash
+python tools/profile_step.py 32 3 vg > gpurun_out/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:warp_photo_roles -s 1 -c 1 -f -o gpurun_out/prof_r2_roles python tools/profile_step.py 32 3 vg > gpurun_out/ncu.log 2>&1
+tail -1 gpurun_out/ncu.log
