@@ -456,8 +456,8 @@ def test_multi_source_single_launch_equals_per_frame_sweeps(B, S, H, W, pad):
 @pytest.mark.parametrize("B,H,W,disp", [(2, 48, 64, False), (1, 9, 12, False), (3, 120, 160, True), (2, 480, 640, False), (1, 271, 480, False)])
 def test_role_split_kernel_equals_classic_kernel(monkeypatch, B, H, W, disp):
     """E2E_ROLES=1 runs the lean value + gradient sweep on warp_photo_roles_kernel (three warp groups, progress mbarriers, 8-step
-    rings -- DESIGN.md section 5) instead of the classic streaming kernel: same strip walk and per-pixel arithmetic, so loss,
-    grad_depth and grad_P are bit-identical and grad_src differs only by the order of the red.global.add atomics."""
+    rings, two centre columns per statistics thread -- DESIGN.md section 5) instead of the classic streaming kernel: same strip
+    walk and per-pixel forward arithmetic."""
     import e2e_slam_b200 as e2e
     from e2e_slam_b200 import ops
     from e2e_slam_b200.synthetic import make_pairs
@@ -481,7 +481,9 @@ def test_role_split_kernel_equals_classic_kernel(monkeypatch, B, H, W, disp):
 
     l0, gd0, gs0, gt0 = run(False)
     l1, gd1, gs1, gt1 = run(True)
-    assert float(l0) == float(l1)
-    assert torch.equal(gd0, gd1)
-    assert torch.equal(gt0, gt1)
+    # per-pixel values are the classic kernel's bits; the loss differs only by the order of the fp32 partial sums (the statistics
+    # threads own two columns each), the gradients by the packed evaluation of the adjoint coefficients
+    assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0))
+    assert rel_max(gd1.cpu().numpy(), gd0.cpu().numpy()) <= 2e-6
+    assert rel_max(gt1.cpu().numpy(), gt0.cpu().numpy()) <= 1e-5
     assert rel_max(gs1.cpu().numpy(), gs0.cpu().numpy()) <= 2e-6
