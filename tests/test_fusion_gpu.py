@@ -364,7 +364,7 @@ def _knn_both(q, r, T=None):
 
 
 @pytest.mark.parametrize("case", ["uniform", "surface", "clustered", "duplicates", "far_queries", "all_far", "off_surface", "line", "single",
-                                  "nonfinite", "slanted_far", "box_edges"])
+                                  "nonfinite", "slanted_far", "box_edges", "plane", "huge_extent"])
 def test_grid_knn_equals_brute_force(case):
     """The uniform-grid kernel must return the brute-force kernel's answer bit for bit (same distance arithmetic, lowest
     index among exact ties) whatever the shape of the clouds."""
@@ -402,6 +402,12 @@ def test_grid_knn_equals_brute_force(case):
         q = torch.zeros(4000, 3, device="cuda"); q[:, 0] = rnd(4000) * 12 - 1; q[:, 1] = 0.01 * rnd(4000)
     elif case == "single":
         r, q = rnd(1, 3), rnd(100, 3) * 5
+    elif case == "plane":                       # exactly flat: one cell along z, the coarse-major ids are padded to whole coarse cells
+        r = torch.cat([rnd(90000, 2) * 6, torch.full((90000, 1), 1.25, device="cuda")], 1)
+        q = torch.cat([rnd(8000, 2) * 7 - 0.5, 1.25 + 0.3 * (rnd(8000, 1) - 0.5)], 1)
+    elif case == "huge_extent":                 # two far-apart blobs: the cell size is enlarged until the padded grid fits
+        r = torch.cat([rnd(40000, 3) * 0.5, rnd(40000, 3) * 0.5 + 5000.0])
+        q = torch.cat([rnd(3000, 3) * 0.6, rnd(3000, 3) * 0.6 + 5000.0, rnd(500, 3) * 5000.0])
     elif case == "slanted_far":                 # a steep, thick sheet and queries 0-60 cm off it: long ring walks, tight coarse boxes
         uv = rnd(300000, 2) * 4 - 2
         r = torch.stack([uv[:, 0], uv[:, 1], 3.0 + 0.9 * uv[:, 0] - 0.6 * uv[:, 1]], 1) + 0.01 * (rnd(300000, 3) - 0.5)
