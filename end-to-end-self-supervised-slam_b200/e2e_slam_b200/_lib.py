@@ -76,6 +76,10 @@ _SIGNATURES = {
     "e2e_knn1_grid_query": (_I, [_P, _P, _LL, _LL, _P, _P, _P, _P]),
     "e2e_icp_workspace_bytes": (_SZ, [_LL, _LL]),
     "e2e_icp_point_to_plane": (_I, [_P, _LL, _P, _P, _LL, _P, _I, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P, _SZ, _P]),
+    "e2e_icp_history_bytes": (_SZ, [_LL, _I]),
+    "e2e_icp_point_to_plane_saved": (_I, [_P, _LL, _P, _P, _LL, _P, _I, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _SZ, _P, _SZ, _P]),
+    "e2e_icp_backward_workspace_bytes": (_SZ, [_LL]),
+    "e2e_icp_backward": (_I, [_P, _LL, _P, _P, _LL, _P, _I, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "e2e_fusion_sequence_workspace_bytes": (_SZ, [_I, _I, _LL]),
     "e2e_fusion_sequence": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _LL, _LL, _P, _SZ, _P]),
     "e2e_fusion_sequence_batch_workspace_bytes": (_SZ, [_I, _I, _I, _LL]),

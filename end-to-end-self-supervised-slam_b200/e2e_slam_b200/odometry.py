@@ -3,11 +3,13 @@
 `se3_exp`) -- what PointFusion runs when `odom` is "icp" / "gradicp", the reference's shipped default
 (configs/config.yaml:30-34; train_depth.py:111-116, 378-381; online_adaption.py:362-363).
 
-Two routes, same conventions (frozen in oracle/icp_oracle.py; gradslam itself is not vendored by the reference):
-  * no autograd: the whole iteration loop runs inside the library (e2e_icp_point_to_plane: exact grid kNN (target gridded once per call), fused
-    Jacobian + normal equations, device-side 6x6 solve and se3 exponential, no host synchronisation);
-  * autograd (GradICP's purpose: poses differentiable w.r.t. the live depth): the same iteration written with torch
-    ops around the library's kNN kernel (the correspondences are constants, as in gradslam).
+One route, with or without autograd (conventions frozen in oracle/icp_oracle.py; gradslam itself is not vendored by the reference):
+the whole iteration loop runs inside the library (e2e_icp_point_to_plane: exact grid kNN (target gridded once per call), fused
+Jacobian + normal equations, device-side 6x6 solve and se3 exponential, no host synchronisation).  With autograd (GradICP's
+purpose: poses differentiable w.r.t. the live depth) the same loop also records its history (e2e_icp_point_to_plane_saved) and
+`backward()` is the library's reverse sweep (e2e_icp_backward: four launches per iteration; the correspondences are constants
+of the derivative, as in gradslam).  The iteration written with torch ops around the kNN kernel (`*_torch`) is kept as the
+autograd reference the tests compare against.
 There is no CPU route: tensors must be CUDA fp32.
 """
 import ctypes
@@ -106,6 +108,57 @@ def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(t.requires_grad for t in ts)
 
 
+class _ICPFunction(torch.autograd.Function):
+    """The library's iteration loop as a differentiable operation: (src [N,3], tgt [M,3], normals [M,3], T0 [4,4]) -> (T [4,4], idx [N])."""
+
+    @staticmethod
+    def forward(ctx, src, tgt, nrm, T0, numiters, damp, dist_thresh, grad_icp, lambda_max, B, B2, nu):
+        src, tgt, nrm, T0 = src.contiguous(), tgt.contiguous(), nrm.contiguous(), f32(T0, "initial_transform").contiguous()
+        dev = src.device
+        N, M = src.shape[0], tgt.shape[0]
+        numiters = int(numiters)
+        T_out = torch.empty(4, 4, dtype=torch.float32, device=dev)
+        idx = torch.zeros(N, dtype=torch.int64, device=dev) if numiters <= 0 else torch.empty(N, dtype=torch.int64, device=dev)
+        nws, nh = lib().e2e_icp_workspace_bytes(N, M), lib().e2e_icp_history_bytes(N, numiters)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        hist = torch.empty(nh, dtype=torch.uint8, device=dev)
+        thr = -1.0 if dist_thresh is None else float(dist_thresh)
+        with torch.cuda.device(dev):
+            check(lib().e2e_icp_point_to_plane_saved(ptr(src), N, ptr(tgt), ptr(nrm), M, ptr(T0), numiters, ctypes.c_float(damp),
+                                                     ctypes.c_float(thr), int(grad_icp), ctypes.c_float(lambda_max), ctypes.c_float(B),
+                                                     ctypes.c_float(B2), ctypes.c_float(nu), ptr(T_out), ptr(idx), ptr(ws), nws,
+                                                     ptr(hist), nh, stream_ptr()), "e2e_icp_point_to_plane_saved")
+        ctx.save_for_backward(src, tgt, nrm, T0, hist)
+        ctx.params = (numiters, float(damp), thr, int(grad_icp), float(lambda_max), float(B), float(B2), float(nu))
+        ctx.mark_non_differentiable(idx)
+        return T_out, idx
+
+    @staticmethod
+    def backward(ctx, gT, _gidx):
+        src, tgt, nrm, T0, hist = ctx.saved_tensors
+        numiters, damp, thr, grad_icp, lambda_max, B, B2, nu = ctx.params
+        dev = src.device
+        N, M = src.shape[0], tgt.shape[0]
+        need = ctx.needs_input_grad
+        gT = f32(gT, "grad_T").contiguous()
+        g_src = torch.empty_like(src)
+        g_tgt = torch.zeros_like(tgt) if need[1] else None      # accumulated with atomics
+        g_nrm = torch.zeros_like(nrm) if need[2] else None
+        g_T0 = torch.empty(4, 4, dtype=torch.float32, device=dev) if need[3] else None
+        nws = lib().e2e_icp_backward_workspace_bytes(N)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().e2e_icp_backward(ptr(src), N, ptr(tgt), ptr(nrm), M, ptr(T0), numiters, ctypes.c_float(damp), ctypes.c_float(thr),
+                                         grad_icp, ctypes.c_float(lambda_max), ctypes.c_float(B), ctypes.c_float(B2), ctypes.c_float(nu),
+                                         ptr(hist), ptr(gT), ptr(g_src), ptr(g_tgt), ptr(g_nrm), ptr(g_T0), ptr(ws), nws, stream_ptr()),
+                  "e2e_icp_backward")
+        return (g_src if need[0] else None), g_tgt, g_nrm, g_T0, None, None, None, None, None, None, None, None
+
+
+def _library_icp_autograd(src_pc, tgt_pc, tgt_normals, initial_transform, numiters, damp, dist_thresh, grad_icp, lambda_max, B, B2, nu):
+    return _ICPFunction.apply(src_pc[0], tgt_pc[0], tgt_normals[0], initial_transform, numiters, damp, dist_thresh, grad_icp, lambda_max, B, B2, nu)
+
+
 def point_to_plane_ICP(src_pc, tgt_pc, tgt_normals, initial_transform, numiters=20, damp=1e-8, dist_thresh=None):
     """Gauss-Newton point-to-plane ICP.  src_pc (1,Ns,3), tgt_pc / tgt_normals (1,Nt,3), initial_transform (4,4).
     Returns (transform (4,4) aligning src to tgt, chamfer_indices of the last iteration)."""
@@ -114,6 +167,13 @@ def point_to_plane_ICP(src_pc, tgt_pc, tgt_normals, initial_transform, numiters=
         raise ValueError(f"initial_transform should have shape (4, 4). Got {tuple(initial_transform.shape)}.")
     if not _needs_grad(src_pc, tgt_pc, tgt_normals, initial_transform):
         return _library_icp(src_pc, tgt_pc, tgt_normals, initial_transform, numiters, damp, dist_thresh, 0, 0.0, 1.0, 1.0, 1.0)
+    return _library_icp_autograd(src_pc, tgt_pc, tgt_normals, initial_transform, numiters, damp, dist_thresh, 0, 0.0, 1.0, 1.0, 1.0)
+
+
+def point_to_plane_ICP_torch(src_pc, tgt_pc, tgt_normals, initial_transform, numiters=20, damp=1e-8, dist_thresh=None):
+    """The same iteration as torch ops around the kNN kernel (autograd by torch): the reference the library's reverse sweep is
+    tested against."""
+    _check_clouds(src_pc, tgt_pc, tgt_normals)
     T = initial_transform
     cur = _apply(T, src_pc[0])
     idx = None
@@ -136,6 +196,13 @@ def point_to_plane_gradICP(src_pc, tgt_pc, tgt_normals, initial_transform, numit
         raise ValueError("nu must be non-zero")
     if not _needs_grad(src_pc, tgt_pc, tgt_normals, initial_transform):
         return _library_icp(src_pc, tgt_pc, tgt_normals, initial_transform, numiters, damp, dist_thresh, 1, lambda_max, B, B2, nu)
+    return _library_icp_autograd(src_pc, tgt_pc, tgt_normals, initial_transform, numiters, damp, dist_thresh, 1, lambda_max, B, B2, nu)
+
+
+def point_to_plane_gradICP_torch(src_pc, tgt_pc, tgt_normals, initial_transform, numiters=20, damp=1e-8, dist_thresh=None,
+                                 lambda_max=2.0, B=1.0, B2=1.0, nu=200.0):
+    """GradICP as torch ops around the kNN kernel (autograd by torch): the reference the library's reverse sweep is tested against."""
+    _check_clouds(src_pc, tgt_pc, tgt_normals)
     T = initial_transform
     cur = _apply(T, src_pc[0])
     lam, lam_min = damp, damp

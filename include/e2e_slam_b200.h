@@ -386,6 +386,28 @@ int e2e_icp_point_to_plane(const float *src, long long N, const float *tgt, cons
                            int grad_icp, float lambda_max, float B, float B2, float nu,
                            float *T_out, long long *idx_out, float *errs, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same alignment as a DIFFERENTIABLE operation (GradICP's purpose: the pose is differentiable w.r.t. the live depth;
+ * gradslam gets it from autograd through its torch ops, online_adaption.py:362-363 with odom = "gradicp").
+ * e2e_icp_point_to_plane_saved runs the identical loop and leaves in `history` (e2e_icp_history_bytes(N, numiters)) what the
+ * reverse sweep needs: per iteration the step, damping, gate, normal equations and transforms, the source cloud before the
+ * step, both sets of correspondences (constants of the derivative, as in gradslam).  e2e_icp_backward then propagates
+ * grad_T_out [4x4, the last row is ignored] to grad_src [N,3] (written), grad_tgt / grad_normals [M,3] (ACCUMULATED with atomics:
+ * pass zeroed buffers, or NULL to skip) and grad_T_init [4x4] (nullable): four launches per iteration, no host synchronisation;
+ * the derivative of the se3 exponential is taken with float64 dual numbers on the device. */
+size_t e2e_icp_history_bytes(long long N, int numiters);
+int e2e_icp_point_to_plane_saved(const float *src, long long N, const float *tgt, const float *tgt_normals, long long M,
+                                 const float *T_init, int numiters, float damp, float dist_thresh,
+                                 int grad_icp, float lambda_max, float B, float B2, float nu,
+                                 float *T_out, long long *idx_out, void *workspace, size_t workspace_bytes,
+                                 void *history, size_t history_bytes, void *stream);
+size_t e2e_icp_backward_workspace_bytes(long long N);
+int e2e_icp_backward(const float *src, long long N, const float *tgt, const float *tgt_normals, long long M,
+                     const float *T_init, int numiters, float damp, float dist_thresh,
+                     int grad_icp, float lambda_max, float B, float B2, float nu,
+                     const void *history, const float *grad_T_out,
+                     float *grad_src, float *grad_tgt, float *grad_normals, float *grad_T_init,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 /* k-th smallest (0-based) of n fp32 values by radix select: four rounds of an 8-bit histogram + pick, nothing is sorted and the host
  * is never synchronised.  torch.median(x) (online_adaption.py:295) is k = (n-1)/2; a NaN anywhere gives NaN, as torch does.
  * median(1 / disp) of a positive disparity map is 1 / (the n/2-th smallest disparity) exactly (x -> RN(1/x) is monotone), so the

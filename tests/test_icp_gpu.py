@@ -53,6 +53,43 @@ def test_library_icp_matches_oracle_and_recovers_motion(grad_icp):
     assert (idx.cpu().numpy() == idx_ref).mean() > 0.995                  # correspondences of the last iteration (near-ties may differ)
 
 
+@pytest.mark.parametrize("grad_icp,thresh", [(True, None), (False, None), (True, 0.02), (False, 0.004)])
+def test_library_reverse_sweep_matches_torch_autograd(grad_icp, thresh):
+    """e2e_icp_backward (the reverse sweep of the device-side loop) against torch autograd through the same iteration written with
+    torch ops (`*_torch`): gradients w.r.t. the source cloud, the target cloud, the target normals and the initial transform of a
+    random linear functional of the recovered pose.  Both routes treat the correspondences as constants."""
+    from e2e_slam_b200 import odometry
+    src, tgt, tn, _ = _scene(n_tgt=3000, n_src=600, seed=3)
+    # 2 mm of noise on the source cloud: without it the residuals vanish at convergence and the derivatives w.r.t. the target
+    # normals are rounding noise (1e-8) on both routes
+    src = (src + np.random.default_rng(7).normal(0.0, 2e-3, size=src.shape)).astype(np.float32)
+    c = lambda a: torch.from_numpy(a).cuda()[None]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    wgt = torch.randn(3, 4, generator=g, device="cuda")
+    T0 = torch.eye(4, device="cuda")
+    T0[:3, 3] = torch.tensor([0.004, -0.003, 0.002], device="cuda")
+    kw = dict(numiters=6, dist_thresh=thresh)
+    if grad_icp:
+        kw.update(nu=0.05)
+    out = []
+    for route in ("lib", "torch"):
+        leaves = [c(src).requires_grad_(True), c(tgt).requires_grad_(True), c(tn).requires_grad_(True), T0.clone().requires_grad_(True)]
+        name = ("point_to_plane_gradICP" if grad_icp else "point_to_plane_ICP") + ("_torch" if route == "torch" else "")
+        T, idx = getattr(odometry, name)(*leaves, **kw)
+        (T[:3] * wgt).sum().backward()
+        out.append((T.detach(), idx, [l.grad for l in leaves]))
+    (T_l, idx_l, g_l), (T_t, idx_t, g_t) = out
+    assert (T_l - T_t).abs().max() <= 2e-5
+    assert (idx_l == idx_t).float().mean() > 0.99
+    g_l[3], g_t[3] = g_l[3][:3], g_t[3][:3]      # the last row of a rigid transform is constant: the library returns 0 for it
+    for name, a, b in zip(("src", "tgt", "normals", "T_init"), g_l, g_t):
+        assert a is not None and bool(torch.isfinite(a).all())
+        scale = float(b.abs().max())
+        assert scale > 1e-6, (name, scale)
+        err = float((a - b).abs().max()) / scale
+        assert err <= 2e-3, (name, err)          # fp32 normal equations on both sides, float64 solve / exponential in ours
+
+
 def test_torch_route_matches_library_and_is_differentiable():
     from e2e_slam_b200 import odometry
     src, tgt, tn, _ = _scene(n_tgt=3000, n_src=600, seed=3)
@@ -70,6 +107,9 @@ def test_torch_route_matches_library_and_is_differentiable():
     s2 = c(src).requires_grad_(True)
     T2, _ = odometry.point_to_plane_ICP(s2, c(tgt), c(tn), eye, numiters=8)
     assert (T2.detach() - T_icp).abs().max() <= 2e-5
+    st = c(src).requires_grad_(True)
+    Tt, _ = odometry.point_to_plane_gradICP_torch(st, c(tgt), c(tn), eye, numiters=8, nu=0.05)
+    assert (Tt.detach() - T_lib).abs().max() <= 2e-5
     # finite-difference check of d(translation sum)/d(one source coordinate) through the differentiable route
     with torch.no_grad():
         eps = 1e-3

@@ -22,3 +22,19 @@ for name, fn in (("icp", lambda: odometry.point_to_plane_ICP(src[None], tgt[None
             T, _ = fn()
         torch.cuda.synchronize()
     print(f"{name}: {(time.perf_counter() - t0) / 5 * 1e3:.2f} ms per 20-iteration alignment, t = {T[:3, 3].tolist()}")
+
+# with autograd: the library's loop + reverse sweep against the iteration written with torch ops
+for name, fn in (("gradicp library fwd+bwd", odometry.point_to_plane_gradICP), ("gradicp torch-op fwd+bwd", odometry.point_to_plane_gradICP_torch),
+                 ("icp library fwd+bwd", odometry.point_to_plane_ICP), ("icp torch-op fwd+bwd", odometry.point_to_plane_ICP_torch)):
+    kw = dict(nu=0.05) if "gradicp" in name else {}
+    def run():
+        s = src[None].clone().requires_grad_(True)
+        T, _ = fn(s, tgt[None], n[None], eye, 20, **kw)
+        T[:3].sum().backward()
+        return s.grad
+    run(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        g = run()
+    torch.cuda.synchronize()
+    print(f"{name}: {(time.perf_counter() - t0) / 3 * 1e3:.2f} ms, |grad| = {float(g.abs().sum()):.4f}")
