@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(SV_NT) smooth_vg_kernel(const SmoothVG p)
 }
 
 // per image: {x sum, y sum} and the backward scalars inv = 1 / me, corr = dot / (me^2 HW); one warp per image, fixed order
-__global__ void __launch_bounds__(32) smooth_stats_kernel(const double *partial, int ctas, const float *me, int HW, double *sums, float *stats)
+// (raw = the disparity was not normalised here: inv = 1, no correction term)
+__global__ void __launch_bounds__(32) smooth_stats_kernel(const double *partial, int ctas, const float *me, int HW, double *sums, float *stats, int raw)
 {
     double t[3] = {0.0, 0.0, 0.0};
     for (int i = threadIdx.x; i < ctas; i += 32)
@@ -177,8 +178,8 @@ __global__ void __launch_bounds__(32) smooth_stats_kernel(const double *partial,
         const float m = me[blockIdx.x];
         sums[blockIdx.x * 2] = t[0];
         sums[blockIdx.x * 2 + 1] = t[1];
-        stats[blockIdx.x * 2] = 1.0f / m;
-        stats[blockIdx.x * 2 + 1] = (float)(t[2] / ((double)m * (double)m * (double)HW));
+        stats[blockIdx.x * 2] = raw ? 1.0f : 1.0f / m;
+        stats[blockIdx.x * 2 + 1] = raw ? 0.0f : (float)(t[2] / ((double)m * (double)m * (double)HW));
     }
 }
 
@@ -188,6 +189,12 @@ __global__ void __launch_bounds__(32) smooth_loss_kernel(const double *sums, int
     for (int i = threadIdx.x; i < B; i += 32) { tx += sums[i * 2]; ty += sums[i * 2 + 1]; }
     tx = warp_sum_d(tx); ty = warp_sum_d(ty);
     if (threadIdx.x == 0) loss[0] = (float)(tx * inv_nx + ty * inv_ny);
+}
+
+__global__ void smooth_ones_kernel(float *me, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) me[i] = 1.0f;          // x / 1 is x: the sweep then works on the disparity as given
 }
 
 __global__ void __launch_bounds__(256) smooth_apply_kernel(const float *gn, const float *stats, const float *grad_loss, int HW, float *grad_disp)
@@ -219,8 +226,8 @@ size_t e2e_smooth_vg_workspace_bytes(int B, int H, int W)
     return sv_a256((size_t)B * sv_sum_blocks(H * W) * 8) + sv_a256((size_t)B * 4) + sv_a256((size_t)B * ctas * 3 * 8) + sv_a256((size_t)B * 2 * 8) + 256;
 }
 
-int e2e_smooth_vg(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
-                  float *loss, float *gn, float *stats, void *workspace, size_t workspace_bytes, void *stream)
+static int smooth_vg_run(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
+                         float *loss, float *gn, float *stats, void *workspace, size_t workspace_bytes, void *stream, int raw)
 {
     cudaStream_t st = (cudaStream_t)stream;
     E2E_REQUIRE(disp && img && img_strides && loss && gn && stats && workspace, "smooth_vg: null argument");
@@ -239,13 +246,29 @@ int e2e_smooth_vg(const float *disp, const float *img, const int64_t img_strides
     p.disp = disp; p.img = make_view(img, img_strides); p.B = B; p.H = H; p.W = W; p.me = me;
     p.cx = (float)(1.0 / ((double)B * H * (W - 1))); p.cy = (float)(1.0 / ((double)B * (H - 1) * W));
     p.gn = gn; p.partial = partial;
-    smooth_sum_kernel<<<dim3(nsum, B), 256, 0, st>>>(disp, HW, sum_partial);
-    smooth_me_kernel<<<B, 32, 0, st>>>(sum_partial, nsum, HW, me);
+    if (raw) {
+        smooth_ones_kernel<<<(B + 255) / 256, 256, 0, st>>>(me, B);
+    } else {
+        smooth_sum_kernel<<<dim3(nsum, B), 256, 0, st>>>(disp, HW, sum_partial);
+        smooth_me_kernel<<<B, 32, 0, st>>>(sum_partial, nsum, HW, me);
+    }
     smooth_vg_kernel<<<grid, SV_NT, 0, st>>>(p);
-    smooth_stats_kernel<<<B, 32, 0, st>>>(partial, ctas, me, HW, sums, stats);
+    smooth_stats_kernel<<<B, 32, 0, st>>>(partial, ctas, me, HW, sums, stats, raw);
     smooth_loss_kernel<<<1, 32, 0, st>>>(sums, B, 1.0 / ((double)B * H * (W - 1)), 1.0 / ((double)B * (H - 1) * W), loss);
-    count_launch(5);
+    count_launch(raw ? 4 : 5);
     return finish_launch("smooth_vg");
+}
+
+int e2e_smooth_vg(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
+                  float *loss, float *gn, float *stats, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return smooth_vg_run(disp, img, img_strides, B, H, W, loss, gn, stats, workspace, workspace_bytes, stream, 0);
+}
+
+int e2e_smooth_vg_raw(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
+                      float *loss, float *gn, float *stats, void *workspace, size_t workspace_bytes, void *stream)
+{
+    return smooth_vg_run(disp, img, img_strides, B, H, W, loss, gn, stats, workspace, workspace_bytes, stream, 1);
 }
 
 int e2e_smooth_apply(const float *gn, const float *stats, const float *grad_loss, int B, int H, int W, float *grad_disp, void *stream)

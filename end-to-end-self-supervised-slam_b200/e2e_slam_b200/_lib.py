@@ -55,6 +55,7 @@ _SIGNATURES = {
     "e2e_smooth_vg_workspace_bytes": (_SZ, [_I, _I, _I]),
     "e2e_smooth_vg": (_I, [_P, _P, _S, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "e2e_smooth_apply": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "e2e_smooth_vg_raw": (_I, [_P, _P, _S, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "e2e_sparse_l1_fwd": (_I, [_P, _P, _P, _LL, _P, _P, _SZ, _P]),
     "e2e_sparse_l1_bwd": (_I, [_P, _P, _P, _LL, _P, _P, _P]),
     "e2e_depth_reg_fwd": (_I, [_P, _P, _LL, _I, _P, _P, _SZ, _P]),

@@ -48,22 +48,25 @@ _SMOOTH_FUSED = os.environ.get("E2E_SMOOTH_FUSED", "1") != "0"
 
 class _Smooth(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, disp, img):
+    def forward(ctx, disp, img, raw=False):
+        """raw: the disparity is used as given (disparity_smoothness_loss of an already normalised disparity)."""
         f32(disp, "disp"), f32(img, "img")
         if disp.dim() != 4 or disp.shape[1] != 1 or img.dim() != 4 or img.shape[1] != 3 or img.shape[2:] != disp.shape[2:]:
             raise ValueError(f"expected disp (B,1,H,W) and img (B,3,H,W), got {tuple(disp.shape)} / {tuple(img.shape)}")
         B, _, H, W = disp.shape
         disp_c = disp.contiguous()
         loss = torch.empty(1, dtype=torch.float32, device=disp.device)
-        ctx.fused = bool(ctx.needs_input_grad[0]) and _SMOOTH_FUSED and H >= 2 and W >= 2
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("the smoothness loss is not differentiated w.r.t. the image (the reference never does)")
+        ctx.fused = (bool(ctx.needs_input_grad[0]) and _SMOOTH_FUSED and H >= 2 and W >= 2) or raw
         if ctx.fused:        # value and d loss / d n in one sweep; backward is one elementwise pass
             gn = torch.empty_like(disp_c)
             stats = torch.empty(B, 2, dtype=torch.float32, device=disp.device)
             n = lib().e2e_smooth_vg_workspace_bytes(B, H, W)
             ws = torch.empty(n, dtype=torch.uint8, device=disp.device)
             with torch.cuda.device(disp.device):
-                check(lib().e2e_smooth_vg(ptr(disp_c), ptr(img), strides4(img), B, H, W, ptr(loss), ptr(gn), ptr(stats), ptr(ws), n,
-                                          stream_ptr()), "e2e_smooth_vg")
+                fn = lib().e2e_smooth_vg_raw if raw else lib().e2e_smooth_vg
+                check(fn(ptr(disp_c), ptr(img), strides4(img), B, H, W, ptr(loss), ptr(gn), ptr(stats), ptr(ws), n, stream_ptr()), "e2e_smooth_vg")
             ctx.save_for_backward(gn, stats)
             return loss.reshape(())
         ws, n = _red_ws(disp.device)
@@ -82,7 +85,7 @@ class _Smooth(torch.autograd.Function):
             g = f32(g, "grad").reshape(1).contiguous()
             with torch.cuda.device(gn.device):
                 check(lib().e2e_smooth_apply(ptr(gn), ptr(stats), ptr(g), B, H, W, ptr(gd), stream_ptr()), "e2e_smooth_apply")
-            return gd, None
+            return gd, None, None
         disp, img = ctx.saved_tensors
         B, _, H, W = disp.shape
         gd = torch.empty_like(disp)
@@ -91,7 +94,7 @@ class _Smooth(torch.autograd.Function):
         with torch.cuda.device(disp.device):
             check(lib().e2e_smooth_bwd(ptr(disp), ptr(img), strides4(img), B, H, W, ptr(g), ptr(gd), ptr(ws), n, stream_ptr()),
                   "e2e_smooth_bwd")
-        return gd, None
+        return gd, None, None
 
 
 def smoothness_loss(disp, img):
@@ -101,15 +104,11 @@ def smoothness_loss(disp, img):
 
 
 def disparity_smoothness_loss(disp, img):
-    """Edge-aware smoothness of an ALREADY normalised disparity (losses.py:119-132), same signature as the
-    reference.  Few-op composition on the GPU; scripts that call compute_smoothness_loss should prefer
-    `smoothness_loss`, which fuses the normalisation and runs in three launches."""
-    f32(disp, "disp"), f32(img, "img")
-    gdx = torch.abs(disp[:, :, :, :-1] - disp[:, :, :, 1:])
-    gdy = torch.abs(disp[:, :, :-1, :] - disp[:, :, 1:, :])
-    gix = torch.mean(torch.abs(img[:, :, :, :-1] - img[:, :, :, 1:]), 1, keepdim=True)
-    giy = torch.mean(torch.abs(img[:, :, :-1, :] - img[:, :, 1:, :]), 1, keepdim=True)
-    return (gdx * torch.exp(-gix)).mean() + (gdy * torch.exp(-giy)).mean()
+    """Edge-aware smoothness of an ALREADY normalised disparity (losses.py:119-132), same signature as the reference: what the
+    unmodified compute_smoothness_loss (train_depth.py:763-773) calls after its own normalisation.  One sweep (value and
+    d loss / d disp, e2e_smooth_vg_raw) + one elementwise pass in backward; scripts that can should call `smoothness_loss`,
+    which also fuses the normalisation."""
+    return _Smooth.apply(disp, img, True)
 
 
 class _EwLoss(torch.autograd.Function):

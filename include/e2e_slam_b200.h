@@ -218,6 +218,11 @@ size_t e2e_smooth_vg_workspace_bytes(int B, int H, int W);
 int e2e_smooth_vg(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
                   float *loss, float *gn, float *stats, void *workspace, size_t workspace_bytes, void *stream);
 int e2e_smooth_apply(const float *gn, const float *stats, const float *grad_loss, int B, int H, int W, float *grad_disp, void *stream);
+/* disparity_smoothness_loss itself (loss/losses.py:119-132) for callers that normalise the disparity on their own, as the
+ * unmodified compute_smoothness_loss does (train_depth.py:763-773): the same sweep on the disparity AS GIVEN; stats = {1, 0}, so
+ * e2e_smooth_apply returns grad_disp = up * gn. */
+int e2e_smooth_vg_raw(const float *disp, const float *img, const int64_t img_strides[4], int B, int H, int W,
+                      float *loss, float *gn, float *stats, void *workspace, size_t workspace_bytes, void *stream);
 
 int e2e_sparse_l1_fwd(const float *pred, const float *mask, const float *gt, long long n, float *loss,
                       void *workspace, size_t workspace_bytes, void *stream);

@@ -91,6 +91,13 @@ def test_smoothness_loss(golden):
     n = d2 / (d2.mean(2, True).mean(3, True) + 1e-7)
     l2 = disparity_smoothness_loss(n, tgt)
     assert abs(float(l2) - float(g["smooth"])) <= RTOL * abs(float(g["smooth"]))
+    # the reference's own composition: compute_smoothness_loss normalises with torch ops (train_depth.py:763-773), then calls
+    # disparity_smoothness_loss -- the kernel of the already normalised disparity, chained through autograd, gives the golden gradient
+    d3 = _d(g, "disp").requires_grad_(True)
+    l3 = disparity_smoothness_loss(d3 / (d3.mean(2, True).mean(3, True) + 1e-7), tgt)
+    l3.backward()
+    assert abs(float(l3) - float(g["smooth"])) <= RTOL * abs(float(g["smooth"]))
+    assert rel_max(d3.grad.cpu().numpy(), g["g_disp_smooth"]) <= RTOL
 
 
 def test_sparse_gt_and_regulariser(golden):
