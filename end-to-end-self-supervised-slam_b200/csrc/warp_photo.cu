@@ -140,6 +140,40 @@ __global__ void __launch_bounds__(256) reduce_gP_kernel(const float *partial, in
     }
 }
 
+// Both reductions of the single-sweep path in ONE launch (a single pair is launch-latency bound: config C1): blocks 0 .. 12 B - 1
+// reduce grad_P as reduce_gP_kernel does, the last block reduces the loss partials.
+__global__ void __launch_bounds__(256) reduce_loss_gP_kernel(const float *loss_partial, long long n, double scale, float *loss,
+                                                             const float *gp_partial, int ctas_per_b, int B, float *gP, const float *skip_flag)
+{
+    __shared__ double sh[8];
+    const bool loss_block = (int)blockIdx.x == 12 * B;
+    if (!loss_block && skip_flag && __ldg(skip_flag) != 0.0f) return;
+    double acc = 0.0;
+    const int b = blockIdx.x / 12, e = blockIdx.x % 12;
+    if (loss_block) {
+        for (long long i = threadIdx.x; i < n; i += 256) acc += (double)loss_partial[i];
+    } else {
+        for (int i = threadIdx.x; i < ctas_per_b; i += 256) acc += (double)gp_partial[((long long)b * ctas_per_b + i) * 12 + e];
+    }
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += sh[i];
+        if (loss_block) loss[0] = (float)(t * scale);
+        else gP[b * 12 + e] = (float)t;
+    }
+}
+
+int launch_reduce_loss_gP(const float *loss_partial, long long n, double scale, float *loss, const float *gp_partial, int ctas_per_b, int B,
+                          float *gP, cudaStream_t st, const float *skip_flag)
+{
+    reduce_loss_gP_kernel<<<B * 12 + 1, 256, 0, st>>>(loss_partial, n, scale, loss, gp_partial, ctas_per_b, B, gP, skip_flag);
+    count_launch();
+    return finish_launch("reduce_loss_gP_kernel");
+}
+
 int launch_reduce_partials(const float *partial, long long n, double scale, float *out, cudaStream_t st)
 {
     reduce_partials_kernel<<<1, 1024, 0, st>>>(partial, n, scale, out);

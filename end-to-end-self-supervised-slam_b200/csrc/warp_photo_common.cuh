@@ -368,6 +368,8 @@ int fill_common(WPParams &p, int B, int C, int H, int W, int padding_mode, int u
 int set_views(WPParams &p, const float *a, const int64_t as[4], const float *b, const int64_t bs[4], int C);
 int launch_reduce_partials(const float *partial, long long n, double scale, float *out, cudaStream_t st);
 int launch_reduce_gP(const float *partial, int ctas_per_b, int B, float *gP, cudaStream_t st, const float *skip_flag = nullptr);
+int launch_reduce_loss_gP(const float *loss_partial, long long n, double scale, float *loss, const float *gp_partial, int ctas_per_b, int B,
+                          float *gP, cudaStream_t st, const float *skip_flag = nullptr);
 // Defined in warp_photo_fused.cu: the streaming value + gradient kernel on a prepared parameter block
 size_t stream_workspace_bytes(int B, int H, int W);
 int launch_stream(WPParams &p, int B, int H, int W, float *loss_mean, float *grad_P, void *workspace, size_t workspace_bytes, cudaStream_t st);
