@@ -164,3 +164,34 @@ def test_pointfusion_tracks_a_sequence_without_ground_truth_poses(odom):
     assert float(err.max()) < 0.03, err
     assert float(err[-1]) < 0.3 * float(drift_if_static[-1])
     assert float((out[:, :3, :3] - poses[:, :3, :3]).abs().max()) < 1e-2
+
+
+def test_gradicp_pose_is_differentiable_wrt_the_live_depth(monkeypatch):
+    """GradICP's purpose (online_adaption.py:362-363 with odom = "gradicp"): the pose PointFusion recovers for a live frame carries
+    a gradient back to that frame's depth map -- through the library's reverse sweep.  The same step with the torch-op iteration in
+    place of the library call (torch autograd end to end) must give the same depth gradient.  (A finite difference of the fp32 pose
+    is too noisy to check a derivative of 2e-3: measured +-3e-4 at a 1 mm step.)"""
+    from e2e_slam_b200 import odometry
+    from e2e_slam_b200.slam import PointFusion, Pointclouds, RGBDImages
+    from e2e_slam_b200.synthetic import room_sequence
+    L, H, W = 2, 120, 160
+    depth, rgb, K, poses = room_sequence(L, H, W, device="cuda")
+    slam = PointFusion(odom="gradicp", dsratio=4, numiters=6, nu=0.05, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    wgt = torch.randn(3, 4, generator=g, device="cuda")
+
+    def depth_grad():
+        rgbd0 = RGBDImages(rgb[None, :1], depth[None, :1, ..., None], K.view(1, 1, 4, 4), poses[None, :1])
+        pc, _ = slam.step(Pointclouds(device="cuda"), rgbd0, None, inplace=False)
+        d1 = depth[1].clone().requires_grad_(True)
+        live = RGBDImages(rgb[None, 1:2], d1[None, None, ..., None], K.view(1, 1, 4, 4), None)
+        pose = slam._localize(pc, live, rgbd0)[0, 0]
+        (pose[:3] * wgt).sum().backward()
+        return pose.detach(), d1.grad
+
+    pose_l, g_l = depth_grad()
+    monkeypatch.setattr(odometry, "point_to_plane_gradICP", odometry.point_to_plane_gradICP_torch)
+    pose_t, g_t = depth_grad()
+    assert (pose_l - pose_t).abs().max() <= 2e-5
+    assert bool(torch.isfinite(g_l).all()) and float(g_t.abs().max()) > 0
+    assert float((g_l - g_t).abs().max()) <= 2e-3 * float(g_t.abs().max())
