@@ -56,7 +56,7 @@ class _WarpPhotometric(torch.autograd.Function):
     synchronisation either way.  E2E_SPECULATE=0 restores forward kernel + unconditional backward kernel."""
 
     @staticmethod
-    def forward(ctx, depth, inv_K, K, T, src, tgt, padding_mode, use_mask, eps, mode, materialise):
+    def forward(ctx, depth, inv_K, K, T, src, tgt, padding_mode, use_mask, eps, mode, materialise, expect_uniform=True):
         f32(depth, "depth"), f32(src, "source frame"), f32(tgt, "target frame")
         if depth.dim() != 4 or depth.shape[1] != 1:
             raise ValueError(f"depth must be (B,1,H,W), got {tuple(depth.shape)}")
@@ -75,7 +75,7 @@ class _WarpPhotometric(torch.autograd.Function):
         syn = valid = pix = loss_map = loss_mean = None
         need_depth, _, need_K, need_T, need_src = ctx.needs_input_grad[:5]
         ctx.spec = None
-        if mode == "map" and _SPECULATE and (need_depth or need_K or need_T or need_src):
+        if mode == "map" and _SPECULATE and expect_uniform and (need_depth or need_K or need_T or need_src):
             loss_map = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
             if materialise:
                 syn = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
@@ -180,7 +180,7 @@ class _WarpPhotometric(torch.autograd.Function):
                 grad_K = torch.zeros_like(K)
                 grad_K[:, :3, :] = torch.matmul(grad_P, T.transpose(1, 2))
         return (grad_depth if need_depth else None, None, grad_K, grad_T, grad_src, None,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 class _WarpPhotometricMean(torch.autograd.Function):
@@ -325,14 +325,16 @@ def warp_photometric_loss_from_disparity(disp, inv_K, K, T, source_frame, target
 
 
 def warp_photometric(depth, inv_K, K, T, source_frame, target_frame, padding_mode="border",
-                     photometric_mask=True, need_outputs=False, eps=1e-7):
+                     photometric_mask=True, need_outputs=False, eps=1e-7, expect_uniform=True):
     """Per-pixel photometric loss of warping `source_frame` into the target view.
 
     Returns loss_map [B,1,H,W]; with need_outputs=True returns (loss_map, synthesized_frame [B,3,H,W],
     valid_mask [B,1,H,W], pixel_coordinates [B,H,W,2]) -- the tensors the reference keeps in `outputs`
-    (train_depth.py:581-590).  Differentiable w.r.t. depth, K, T and source_frame."""
+    (train_depth.py:581-590).  Differentiable w.r.t. depth, K, T and source_frame.
+    expect_uniform=False: the caller knows that the map will NOT be reduced by a plain mean (min-reprojection, auto-masking,
+    per-pixel weights): the forward then skips the speculative gradients and backward runs the gradient-map sweep directly."""
     return _WarpPhotometric.apply(depth, inv_K, K, T, source_frame, target_frame, padding_mode,
-                                  photometric_mask, eps, "map", need_outputs)
+                                  photometric_mask, eps, "map", need_outputs, bool(expect_uniform))
 
 
 def warp_photometric_loss(depth, inv_K, K, T, source_frame, target_frame, padding_mode="border",

@@ -107,13 +107,17 @@ def fused_novel_view_synthesis(self, inputs):
     if self.args.LOSS.geometric:
         raise NotImplementedError("the fused op covers the photometric branch; LOSS.geometric uses the granular ops")
     outputs = {}
+    # min-reprojection / auto-masking send a per-pixel gradient back (the winner of each pixel): no point in the speculative
+    # uniform-gradient sweep then -- forward kernel now, gradient-map sweep in backward
+    uniform = not (getattr(self.args.LOSS, "min_reprojection", False) or getattr(self.args.LOSS, "auto_masking", False))
     for frame in self.args.DATA.frames[1:]:
         T = inputs["T", frame]
         if T.dim() == 4:
             T = T.squeeze(1)                      # online_adaption.py:446
         loss_map, syn, valid, _ = ops.warp_photometric(
             inputs["target_depth"], inputs["Inverse_K"], inputs["K"], T, inputs["source_frame", frame], inputs["target_frame"],
-            padding_mode=self.args.MODEL.padding_mode, photometric_mask=bool(self.args.LOSS.photometric_mask), need_outputs=True)
+            padding_mode=self.args.MODEL.padding_mode, photometric_mask=bool(self.args.LOSS.photometric_mask), need_outputs=True,
+            expect_uniform=uniform)
         outputs[("valid_mask", frame)] = valid
         outputs[("synthesized_frame", frame)] = syn
         outputs[("photometric_map", frame)] = loss_map
