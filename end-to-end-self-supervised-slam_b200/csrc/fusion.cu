@@ -720,6 +720,7 @@ __device__ __forceinline__ void seq_maps(const SeqParams &p, int f, const Cam &c
 struct SeqShared {
     Cam cams[2];
     int wcnt[SEQ_MAX_ITERS * SEQ_NW];      // appended pixels per (sub-block, warp), then exclusive offsets
+    long long wsum[SEQ_NW];                // look-back: per-warp sums of the preceding CTAs' counts
     long long sh_base;
 };
 
@@ -845,9 +846,9 @@ __device__ __forceinline__ void seq_frame(const SeqParams &p, SeqShared &sh, int
     SEQ_STAMP(257 + 4 * s);
     if (s + 1 < p.L) seq_maps<SB ^ 1>(p, s + 1, cams[sb ^ 1], pix0, chunk, iters);   // independent of the map: fills the wait for the other CTAs
     SEQ_STAMP(258 + 4 * s);
-    if (wid == 0) {                                        // sum of the counts of all preceding CTAs (same frame tag)
-        long long before = 0;
-        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+    {                                                      // sum of the counts of all preceding CTAs (same frame tag): every thread
+        long long before = 0;                              // looks at one of them -- one round trip instead of blockIdx.x / 32 in a row
+        for (int b = tid; b < (int)blockIdx.x; b += SEQ_NT) {
             unsigned long long v;
             do v = ld_relaxed_u64(p.counts + b);
             while ((unsigned)(v >> 32) != (unsigned)(s + 1));
@@ -855,7 +856,14 @@ __device__ __forceinline__ void seq_frame(const SeqParams &p, SeqShared &sh, int
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
-        if (lane == 0) sh_base = N + before;
+        if (lane == 0) sh.wsum[wid] = before;
+        __syncthreads();
+        if (wid == 0) {
+            long long t = lane < SEQ_NW ? sh.wsum[lane] : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) sh_base = N + t;
+        }
     }
     __syncthreads();
     SEQ_STAMP(259 + 4 * s);
