@@ -11,11 +11,15 @@
 //   smooth_mean (per-image sum)  ->  smooth_me (mean + 1e-7)  ->  smooth_vg (loss partials, gn = dL/dn, dot = sum gn * disp)
 //   ->  smooth_stats (per image)  ->  smooth_loss;   backward = one elementwise pass  grad = up * (gn / me - dot / (me^2 HW)).
 // Compulsory traffic 4 (mean) + 16 (vg read) + 4 (gn write) + 8 (backward) = 32 B/px.
+#include <cstdint>
+
 #include "common.cuh"
 
 namespace e2e {
 
-constexpr int SV_NT = 128;          // columns per CTA
+constexpr int SV_NT = 128;          // threads per CTA
+constexpr int SV_OWN = 30;          // owner columns per warp: lanes 1..30; lanes 0 and 31 carry the left / right neighbour column
+constexpr int SV_COLS = (SV_NT / 32) * SV_OWN;      // owner columns per CTA
 constexpr int SV_ROWS = 30;         // rows per CTA (480 = 16 x 30)
 
 __global__ void __launch_bounds__(256) smooth_sum_kernel(const float *disp, int HW, double *partial)
@@ -23,7 +27,15 @@ __global__ void __launch_bounds__(256) smooth_sum_kernel(const float *disp, int 
     __shared__ double sh[8];
     const float *d = disp + (long long)blockIdx.y * HW;
     double v = 0.0;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) v += (double)d[i];
+    if ((HW & 3) == 0 && (((uintptr_t)d) & 15u) == 0) {      // 16-byte loads, four per thread in flight
+        const float4 *d4 = reinterpret_cast<const float4 *>(d);
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < HW / 4; i += gridDim.x * 256) {
+            const float4 q = d4[i];
+            v += ((double)q.x + (double)q.y) + ((double)q.z + (double)q.w);
+        }
+    } else {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) v += (double)d[i];
+    }
     v = warp_sum_d(v);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
@@ -57,19 +69,13 @@ struct SPix {
     float n, c0, c1, c2;
 };
 
-__device__ __forceinline__ SPix load_pix(const float *d, const ImgView &im, long long ib, int W, int y, int x, float me)
-{
-    const long long o = ib + (long long)y * im.sh + (long long)x * im.sw;
-    SPix p;
-    p.n = xdiv(d[y * W + x], me);
-    p.c0 = im.p[o]; p.c1 = im.p[o + im.sc]; p.c2 = im.p[o + 2 * im.sc];
-    return p;
-}
-
-// exp(-mean_c |a - b|): channels summed in order then / 3 (losses.py:125-126)
+// exp(-mean_c |a - b|): channels summed in order (losses.py:125-126).  The weight is a smooth factor of the loss (contract: 1e-5),
+// so the mean is a multiplication by 1/3 and the exponential the hardware ex2 (2 ulp): an IEEE division and a libm expf per pair were
+// a fifth of this kernel's instructions.  What has to agree with the reference bit for bit is the SIGN of the disparity difference
+// (the gradient flips with it), and that comes from the exactly divided n.
 __device__ __forceinline__ float edge_weight(const SPix &a, const SPix &b)
 {
-    return expf(-(((fabsf(a.c0 - b.c0) + fabsf(a.c1 - b.c1)) + fabsf(a.c2 - b.c2)) / 3.0f));
+    return __expf(-(((fabsf(a.c0 - b.c0) + fabsf(a.c1 - b.c1)) + fabsf(a.c2 - b.c2)) * (1.0f / 3.0f)));
 }
 
 __device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
@@ -78,9 +84,14 @@ __global__ void __launch_bounds__(SV_NT) smooth_vg_kernel(const SmoothVG p)
 {
     __shared__ double sh[SV_NT / 32][3];
     const int b = blockIdx.z, H = p.H, W = p.W;
-    const int x = blockIdx.x * SV_NT + threadIdx.x, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // a warp owns 30 columns and also loads the column on either side of them (6.7 % more loads): every horizontal pair is then formed
+    // from shuffles alone -- the version in which lanes 0 / 31 fetched and normalised their outside neighbour themselves spent a
+    // fifth of the warp's instructions on those two lanes
+    const int x = blockIdx.x * SV_COLS + wid * SV_OWN + lane - 1;
     const int y0 = blockIdx.y * SV_ROWS, y1 = min(y0 + SV_ROWS, H);
-    const bool col = x < W;
+    const bool col = x >= 0 && x < W;
+    const bool own = col && lane >= 1 && lane <= SV_OWN;
     const float *d = p.disp + (long long)b * H * W;
     const long long ib = (long long)b * p.img.sb;
     const float me = p.me[b];
@@ -107,31 +118,21 @@ __global__ void __launch_bounds__(SV_NT) smooth_vg_kernel(const SmoothVG p)
         const bool owned = y >= y0 && y < y1;
         float gx = 0.f, gxl = 0.f;
         if (owned) {      // uniform per CTA
-            // right neighbour: the next lane's pixel; the last lane of a warp loads it
-            SPix r;
+            SPix r;       // right neighbour: the next lane's pixel
             r.n = __shfl_down_sync(0xffffffffu, c.n, 1);
             r.c0 = __shfl_down_sync(0xffffffffu, c.c0, 1);
             r.c1 = __shfl_down_sync(0xffffffffu, c.c1, 1);
             r.c2 = __shfl_down_sync(0xffffffffu, c.c2, 1);
-            if (lane == 31 && x + 1 < W) r = load_pix(d, p.img, ib, W, y, x + 1, me);
-            if (col && x + 1 < W) {
+            if (col && lane < 31 && x + 1 < W) {
                 const float e = edge_weight(c, r), df = xsub(c.n, r.n);      // explicitly rounded: both pixels of a pair agree on the sign
-                sx += fabsf(df) * e;
+                if (own) sx += fabsf(df) * e;                                   // a pair is counted by its left pixel
                 gx = p.cx * sgnf(df) * e;
             }
-            // the pair with the left neighbour: the previous lane's gx; the first lane of a warp forms it itself
-            gxl = __shfl_up_sync(0xffffffffu, gx, 1);
-            if (lane == 0) {
-                gxl = 0.f;
-                if (col && x > 0) {
-                    const SPix l = load_pix(d, p.img, ib, W, y, x - 1, me);
-                    gxl = p.cx * sgnf(xsub(l.n, c.n)) * edge_weight(l, c);
-                }
-            }
+            gxl = __shfl_up_sync(0xffffffffu, gx, 1);      // the pair with the left neighbour (lane 0's own left pair is nobody's business here)
         }
         // the pair (y-1, y): closes gn of row y-1
         float gy = 0.f;
-        if (col && y > max(y0 - 1, 0)) {
+        if (own && y > max(y0 - 1, 0)) {
             const float e = edge_weight(up, c), df = xsub(up.n, c.n);
             gy = p.cy * sgnf(df) * e;
             if (y - 1 >= y0) {                       // the pair belongs to the segment that owns its upper pixel
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(SV_NT) smooth_vg_kernel(const SmoothVG p)
         up = c;
         d_prev = dv;
     }
-    if (col && y1 == H) {                            // the last image row has no pair below it
+    if (own && y1 == H) {                            // the last image row has no pair below it
         p.gn[((long long)b * H + (H - 1)) * W + x] = g_row;
         dot += g_row * d_prev;
     }
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(SV_NT) smooth_vg_kernel(const SmoothVG p)
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         v[k] = warp_sum_d(v[k]);
-        if (lane == 0) sh[threadIdx.x >> 5][k] = v[k];
+        if (lane == 0) sh[wid][k] = v[k];
     }
     __syncthreads();
     if (threadIdx.x < 3) {
@@ -203,6 +204,15 @@ __global__ void __launch_bounds__(256) smooth_apply_kernel(const float *gn, cons
     const float up = grad_loss ? __ldg(grad_loss) : 1.0f, inv = stats[b * 2], corr = stats[b * 2 + 1];
     const float *g = gn + (long long)b * HW;
     float *o = grad_disp + (long long)b * HW;
+    if ((HW & 3) == 0 && ((((uintptr_t)g) | ((uintptr_t)o)) & 15u) == 0) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(g);
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < HW / 4; i += gridDim.x * 256) {
+            const float4 q = g4[i];
+            o4[i] = make_float4(up * (q.x * inv - corr), up * (q.y * inv - corr), up * (q.z * inv - corr), up * (q.w * inv - corr));
+        }
+        return;
+    }
     for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) o[i] = up * (g[i] * inv - corr);
 }
 
@@ -222,7 +232,7 @@ extern "C" {
 size_t e2e_smooth_vg_workspace_bytes(int B, int H, int W)
 {
     if (B < 1 || H < 1 || W < 1) return 256;
-    const size_t ctas = (size_t)((W + SV_NT - 1) / SV_NT) * ((H + SV_ROWS - 1) / SV_ROWS);
+    const size_t ctas = (size_t)((W + SV_COLS - 1) / SV_COLS) * ((H + SV_ROWS - 1) / SV_ROWS);
     return sv_a256((size_t)B * sv_sum_blocks(H * W) * 8) + sv_a256((size_t)B * 4) + sv_a256((size_t)B * ctas * 3 * 8) + sv_a256((size_t)B * 2 * 8) + 256;
 }
 
@@ -234,7 +244,7 @@ static int smooth_vg_run(const float *disp, const float *img, const int64_t img_
     E2E_REQUIRE(B >= 1 && H >= 2 && W >= 2 && B <= 65535, "smooth_vg: needs H, W >= 2 (the means over H*(W-1) and (H-1)*W pairs)");
     E2E_REQUIRE(workspace_bytes >= e2e_smooth_vg_workspace_bytes(B, H, W), "smooth_vg: workspace too small");
     const int HW = H * W, nsum = sv_sum_blocks(HW);
-    const dim3 grid((W + SV_NT - 1) / SV_NT, (H + SV_ROWS - 1) / SV_ROWS, B);
+    const dim3 grid((W + SV_COLS - 1) / SV_COLS, (H + SV_ROWS - 1) / SV_ROWS, B);
     E2E_REQUIRE(grid.y <= 65535, "smooth_vg: image too tall");
     const int ctas = (int)(grid.x * grid.y);
     unsigned char *w = (unsigned char *)workspace;
