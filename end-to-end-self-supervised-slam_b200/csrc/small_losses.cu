@@ -2,6 +2,8 @@
 // depth regulariser, geometric consistency.  Each is a grid-stride pass (grid = a multiple of the SM
 // count) producing per-CTA partial sums in double, followed by a one-CTA deterministic final reduce;
 // nothing synchronises with the host.
+#include <cstdint>
+
 #include "common.cuh"
 
 namespace e2e {
@@ -180,16 +182,27 @@ template <int KIND>
 __global__ void __launch_bounds__(RED_NT) ew_fwd_kernel(const float *a, const float *b, const float *c, long long n, double *partial)
 {
     double v[2] = {0.0, 0.0};
-    for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT) {
-        if (KIND == EW_SPARSE_L1) v[0] += (double)fabsf(a[i] * b[i] - c[i]);                 // a=pred b=mask c=gt
-        if (KIND == EW_REG_L1) v[0] += (double)fabsf(a[i] - b[i]);                           // a=initial b=refined
-        if (KIND == EW_REG_L2) { const float t = a[i] - b[i]; v[0] += (double)(t * t); }
+    auto term = [&](float ai, float bi, float ci) {
+        if (KIND == EW_SPARSE_L1) v[0] += (double)fabsf(ai * bi - ci);                      // a=pred b=mask c=gt
+        if (KIND == EW_REG_L1) v[0] += (double)fabsf(ai - bi);                              // a=initial b=refined
+        if (KIND == EW_REG_L2) { const float t = ai - bi; v[0] += (double)(t * t); }
         if (KIND == EW_GEOMETRIC) {                                                          // a=warped b=interp c=valid
-            float t = fabsf(a[i] - b[i]) / (a[i] + b[i]);
+            float t = fabsf(ai - bi) / (ai + bi);
             t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);                                        // NaN stays NaN like torch.clamp
-            v[0] += (double)(t * c[i]);
-            v[1] += (double)c[i];
+            v[0] += (double)(t * ci);
+            v[1] += (double)ci;
         }
+    };
+    const bool has_c = (KIND == EW_SPARSE_L1 || KIND == EW_GEOMETRIC);
+    if ((n & 3) == 0 && ((((uintptr_t)a) | ((uintptr_t)b) | (has_c ? (uintptr_t)c : 0)) & 15u) == 0) {      // 16-byte loads
+        const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b), *c4 = reinterpret_cast<const float4 *>(c);
+        for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n / 4; i += (long long)gridDim.x * RED_NT) {
+            const float4 x = a4[i], y = b4[i], z = has_c ? c4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            term(x.x, y.x, z.x); term(x.y, y.y, z.y); term(x.z, y.z, z.z); term(x.w, y.w, z.w);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT)
+            term(a[i], b[i], has_c ? c[i] : 0.f);
     }
     block_partials<2>(v, partial);
 }
@@ -210,17 +223,29 @@ __global__ void __launch_bounds__(RED_NT) ew_bwd_kernel(const float *a, const fl
                                                         const float *grad_loss, float *grad)
 {
     const float g = (grad_loss ? grad_loss[0] : 1.0f) / (float)n;
-    for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT) {
+    auto term = [&](float ai, float bi, float ci) -> float {
         if (KIND == EW_SPARSE_L1) {
-            const float t = a[i] * b[i] - c[i];
-            grad[i] = g * (t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f)) * b[i];
+            const float t = ai * bi - ci;
+            return g * (t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f)) * bi;
         }
         if (KIND == EW_REG_L1) {
-            const float t = b[i] - a[i];
-            grad[i] = g * (t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f));
+            const float t = bi - ai;
+            return g * (t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f));
         }
-        if (KIND == EW_REG_L2) grad[i] = g * 2.0f * (b[i] - a[i]);
+        return g * 2.0f * (bi - ai);      // EW_REG_L2
+    };
+    const bool has_c = (KIND == EW_SPARSE_L1);
+    if ((n & 3) == 0 && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)grad) | (has_c ? (uintptr_t)c : 0)) & 15u) == 0) {      // 16-byte accesses
+        const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b), *c4 = reinterpret_cast<const float4 *>(c);
+        float4 *g4 = reinterpret_cast<float4 *>(grad);
+        for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n / 4; i += (long long)gridDim.x * RED_NT) {
+            const float4 x = a4[i], y = b4[i], z = has_c ? c4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            g4[i] = make_float4(term(x.x, y.x, z.x), term(x.y, y.y, z.y), term(x.z, y.z, z.z), term(x.w, y.w, z.w));
+        }
+        return;
     }
+    for (long long i = (long long)blockIdx.x * RED_NT + threadIdx.x; i < n; i += (long long)gridDim.x * RED_NT)
+        grad[i] = term(a[i], b[i], has_c ? c[i] : 0.f);
 }
 
 // d loss / d {warped, interpolated} of geometric_consistency_loss: loss = sum(t * m) / sum(m) if sum(m) > 10000 else 0,
